@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — frame pairs/s (match + RANSAC) at 5 000 keypoints, 256-bit descriptors, 1 024 hypotheses.
+
+Workload (BASELINE.json configs[1]): every consecutive pair of a synthetic monocular sequence with
+5 000 keypoints per frame goes through match_features = Hamming kNN-2 + ratio test + RansacFilter
+(1 024 hypotheses, threshold 10) + inlier copy-out. One STEP = one pass over this rank's sequence
+(--frames frames, frames-1 pairs) in a fixed number of batched kernel launches. Per-rank inputs are
+~205 MB (larger than the 126 MB L2), so consecutive steps do not find their inputs in L2.
+
+  value  pairs/s, inputs resident in HBM (vb_pairs_run_d), CUDA events on the launching stream
+  e2e    pairs/s through the host-pointer C-ABI call (vb_pairs_run): pinned host buffers, H2D of all
+         frames and D2H of results + matches inside the timed region
+  roofline      the scoring kernel k_score (the north star's named kernel), logical 16 B per
+                (hypothesis, match) evaluation against the measured HBM peak; DESIGN.md explains why the
+                kernel is really FP32/FP64-issue bound
+  cpu_baseline  the C oracle (port of the reference path) on the box's host cores, bounded sample
+  --impl reference   times that CPU path with all host threads instead of the GPU path
+
+N > 1 (torchrun): every rank owns its own sequence shard on its own GPU (weak scaling), no data-path
+collective; gloo is used only for the barrier and the max-over-ranks of the device time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "frame pairs/sec (match+RANSAC) at 5k kpts"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1025, help="frames per rank (pairs = frames-1)")
+    ap.add_argument("--kpts", type=int, default=5000)
+    ap.add_argument("--hyps", type=int, default=1024)
+    ap.add_argument("--threshold", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also run the config-5 scoring sweep corner (1M x 16384)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle(native=True):
+    """The checker, used here only as the timed CPU baseline. Rebuilt with -march=native on this box."""
+    from oracle_lib import Oracle, build_oracle
+    path = None
+    if native:
+        try:
+            path = build_oracle(out="_native", march="-march=native")
+        except Exception:
+            path = None
+    return Oracle(path)
+
+
+def cpu_pairs_per_s(orc, pts, desc, npairs, hyps, thr, seed0, threads=0):
+    used = C.c_int()
+    sub_p = np.ascontiguousarray(pts[:npairs + 1])
+    sub_d = np.ascontiguousarray(desc[:npairs + 1])
+    t0 = time.perf_counter()
+    tot = orc.lib.vbo_pairs_run(sub_p, sub_d, npairs + 1, pts.shape[1], desc.shape[2], 0.7, hyps, thr, seed0, threads,
+                                C.byref(used))
+    dt = time.perf_counter() - t0
+    return npairs / dt, used.value, dt, tot
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port: the matcher is an OpenCV call in the
+    reference, so there is no reference source to compile for it) on all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from vslam_b200 import synth
+    orc = cpu_oracle()
+    cores = os.cpu_count() or 1
+    sample = int(min(args.frames - 1, max(2 * cores, 8)))
+    pts, desc = synth.sequence(sample + 1, args.kpts, 1000)
+    for _ in range(args.warmup):
+        cpu_pairs_per_s(orc, pts, desc, min(sample, cores), args.hyps, args.threshold, 1)
+    t0 = time.perf_counter()
+    used = 1
+    for _ in range(args.steps):
+        _, used, _, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 popcount + f32/f64 residual", "data": "synthetic",
+            "config": workload_config(args, sample),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"{sample} pairs per step x {args.steps} steps, OpenMP over pairs"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pairs_per_rank):
+    return {"workload": "BASELINE configs[1]: frame pairs of 5000 keypoints, 256-bit binary descriptors, "
+                        "1024 RANSAC hypotheses (synthetic forward-motion sequence, SURVEY 8d C2/C4)",
+            "kpts": args.kpts, "descriptor_bits": 256, "hypotheses": args.hyps, "threshold": args.threshold, "ratio": 0.7,
+            "pairs_per_step_per_gpu": pairs_per_rank,
+            "l2": "per-rank inputs %.0f MB > 126 MB L2; no explicit flush" % ((pairs_per_rank + 1) * args.kpts * 40 / 1e6)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vslam_b200 import synth
+    from vslam_b200.lib import PAIR_RESULT_DTYPE, Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if world > 1:
+        dist.init_process_group("gloo", init_method="env://")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = Context(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    nframes, k, nbytes = args.frames, args.kpts, 32
+    P = nframes - 1
+    pts, desc = synth.sequence(nframes, k, 1000 + rank)           # every rank owns its own shard (weak scaling)
+    prm = ctx.params(0.7, 8, args.hyps, args.threshold, 1)
+
+    # device-resident inputs / outputs (torch = device memory plumbing only)
+    pts_d = torch.from_numpy(pts).to(dev)
+    desc_d = torch.from_numpy(desc).to(dev)
+    res_d = torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    out_d = torch.zeros((P, k, 2), dtype=torch.int32, device=dev)
+    # pinned host buffers for the e2e leg
+    pts_h = torch.from_numpy(pts).pin_memory()
+    desc_h = torch.from_numpy(desc).pin_memory()
+    res_h = torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    out_h = torch.zeros((P, k, 2), dtype=torch.int32).pin_memory()
+
+    def step_device():
+        ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, pts_d.data_ptr(), desc_d.data_ptr(), nframes, k, nbytes, C.byref(prm),
+                                      res_d.data_ptr(), out_d.data_ptr()))
+
+    def step_e2e():
+        ctx._chk(ctx.L.vb_pairs_run(ctx.h, pts_h.data_ptr(), desc_h.data_ptr(), nframes, k, nbytes, C.byref(prm),
+                                    res_h.data_ptr(), out_h.data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    value = world * P * args.steps / (ms_total * 1e-3)
+
+    # sanity: the timed path produced real results
+    res = res_d.cpu().numpy().view(PAIR_RESULT_DTYPE)
+    ok_pairs = int((res["status"] == 0).sum())
+    mean_matches = float(res["n_matches"].mean())
+    sum_tent = int(res["n_tentative"].sum())
+
+    # ---- per-kernel device times (one extra profiled step, CUDA events inside the library) -------
+    ctx.profile(True)
+    step_device()
+    torch.cuda.synchronize(dev)
+    kt = {name: ctx.profile_ms(name) for name in ("hamming", "finish", "sample", "solve", "score", "select")}
+    ctx.profile(False)
+    # k_score: profile it over several launches of the timed workload for the roofline figure
+    score_ms = []
+    for _ in range(3):
+        ctx.profile(True)
+        step_device()
+        torch.cuda.synchronize(dev)
+        score_ms.append(ctx.profile_ms("score"))
+        ctx.profile(False)
+    score_ms_avg = float(np.mean(score_ms))
+    peak, peak_src = measured_peaks()
+    evals = float(args.hyps) * float(sum_tent)                    # (hypothesis, match) evaluations per launch
+    logical_bytes = 16.0 * evals + 36.0 * args.hyps * P + 8.0 * args.hyps * P
+    achieved = logical_bytes / (score_ms_avg * 1e-3) / 1e9
+    roofline = {"kernel": "k_score (RANSAC residual / inlier scoring)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "evals_per_launch": evals, "ms_per_launch": score_ms_avg,
+                "hypotheses_scored_per_s": args.hyps * P / (score_ms_avg * 1e-3),
+                "note": "logical bytes = 16 B x hypotheses x matches (SURVEY 8d); tiles are L2/smem resident so DRAM "
+                        "traffic is far lower and the kernel is FP32/FP64-issue bound (DESIGN.md)"}
+    step_ms = ms_total / args.steps
+    shares = {n: (v / step_ms if v and v > 0 else None) for n, v in kt.items()}
+
+    # ---- end to end through the host-pointer ABI call -------------------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    res_e = res_h.numpy().view(PAIR_RESULT_DTYPE)
+    assert np.array_equal(res_e["n_matches"], res["n_matches"]), "e2e and device-resident paths disagree"
+    e2e = {"value": world * P * e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(pts_h.numel() * 4 + desc_h.numel()),
+           "d2h_bytes_per_step": int(res_h.numel() + out_h.numel() * 4), "steps": e_steps}
+
+    # ---- single-pair latency through the reference-shaped call (match_features) ------------------
+    fp0 = (pts[0], desc[0], pts[1], desc[1])
+    for _ in range(5):
+        ctx.match_features(*fp0, prm)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.match_features(*fp0, prm)
+    single_ms = (time.perf_counter() - t0) / 20 * 1e3
+
+    # ---- CPU baseline on this box's host cores (rank 0, bounded sample) ---------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        orc = cpu_oracle()
+        cores = os.cpu_count() or 1
+        v1, _, dt1, _ = cpu_pairs_per_s(orc, pts, desc, 2, args.hyps, args.threshold, 1, threads=1)
+        sample = int(min(P, max(cores, 8)))
+        vN, used, dtN, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=0)
+        # parity spot check of the timed GPU output against the same oracle (first pair)
+        o = orc.match_features(pts[0], desc[0], pts[1], desc[1], 0.7, 8, args.hyps, args.threshold, 1)
+        parity = bool(o["n"] == int(res["n_matches"][0]) and o["best"] == int(res["best_hyp"][0]))
+        cpu = {"value": vN, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": f"{sample} pairs over {used} OpenMP threads in {dtN:.1f} s (oracle C port, -O3 -march=native)",
+               "single_thread_pairs_per_s": v1, "host_cpus": cores, "gpu_matches_oracle_on_pair0": parity}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8 popcount + f32/f64 residual", "data": "synthetic",
+                "config": workload_config(args, P), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "kernel_ms": kt, "kernel_share_of_step": shares,
+                "hamming": {"pair_distances_per_s": float(P) * k * k / (kt["hamming"] * 1e-3) if kt["hamming"] > 0 else None,
+                            "popc_per_pair_distance": 4, "note": "integer-pipe bound (XOR+LOP3 CSA+POPC), not HBM"},
+                "single_pair_match_features_ms": single_ms,
+                "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
+                          "mean_tentative": sum_tent / P}}
+        if args.sweep:
+            line["score_sweep"] = score_sweep(ctx, torch, dev, peak)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def score_sweep(ctx, torch, dev, peak):
+    """BASELINE config 5 corners: matches x hypotheses, device-resident, CUDA events."""
+    from oracle_lib import Oracle
+    from vslam_b200 import synth
+    orc = Oracle()
+    out = []
+    rng = np.random.default_rng(0)
+    base = synth.correspondences(4000, 3)
+    for m, h in ((1000, 256), (16384, 1024), (262144, 4096), (1000000, 16384)):
+        corr = synth.correspondences(m, 11)
+        Fs = np.zeros((h, 9), np.float32)
+        nb = min(h, 512)
+        for i in range(nb):
+            sel = rng.choice(len(base), 8, replace=False)
+            Fs[i] = orc.compute_fundamental(base[sel, :2], base[sel, 2:]).reshape(-1)
+        Fs[nb:] = Fs[rng.integers(0, nb, h - nb)]
+        cd, fd = torch.from_numpy(corr).to(dev), torch.from_numpy(Fs).to(dev)
+        cnt = torch.zeros(h, dtype=torch.int32, device=dev)
+        sc = torch.zeros(h, dtype=torch.float32, device=dev)
+        call = lambda: ctx._chk(ctx.L.vb_ransac_score_d(ctx.h, cd.data_ptr(), m, fd.data_ptr(), h, 10.0, cnt.data_ptr(), sc.data_ptr()))
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize(dev)
+        ms = []
+        for _ in range(5):
+            ctx.profile(True)
+            call()
+            torch.cuda.synchronize(dev)
+            ms.append(ctx.profile_ms("score"))
+            ctx.profile(False)
+        t = float(np.mean(ms)) * 1e-3
+        gbs = 16.0 * m * h / t / 1e9
+        out.append({"matches": m, "hypotheses": h, "ms": t * 1e3, "hyp_per_s": h / t, "evals_per_s": m * h / t,
+                    "logical_GBps": gbs, "frac_of_hbm_peak": gbs / peak})
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+/* vslam_b200.h — C ABI of the B200-native correspondence path (libvslam_b200.so).
+ *
+ * This is the drop-in boundary for the reference's frame-to-frame correspondence hot path
+ * (rahulaggarwal965/vslam; file:line below are relative to the reference tree):
+ *
+ *   KD-tree build      construct_kdtree        src/KDTree.cpp:25-35, :107-121   include/KDTree.h:25,60
+ *   KD-tree 1-NN       nearest                 src/KDTree.cpp:37-71             include/KDTree.h:30
+ *   KD-tree radius     radius_search           src/KDTree.cpp:73-101, :145-171  include/KDTree.h:44,79
+ *   descriptor match   match_features (front)  src/Frame.cpp:82-95              include/Frame.h:34
+ *   RANSAC             RansacFilter::*         src/RansacFilter.cpp:6-140       include/RansacFilter.h:9-25
+ *
+ * The reference has no FFI: callers include KDTree.h / RansacFilter.h and link the objects. The
+ * adapters in include/KDTree.h and include/RansacFilter.h of THIS repo keep those C++ interfaces and
+ * forward to the functions below (INTEGRATION.md shows the wiring).
+ *
+ * Conventions
+ *   - plain C types only; every function returns VB_OK (0) or a VB_ERR_* code and writes no output on
+ *     failure. vb_last_error() returns a thread-local message for the last failure.
+ *   - pointers are HOST pointers unless the function name ends in _d, in which case every array
+ *     argument is a DEVICE pointer on the context's GPU and the call only enqueues work on the
+ *     context's stream (call vb_synchronize before reading results).
+ *   - points are (x, y) float pairs; matches / pairs are (first, second) int32 pairs, first indexing
+ *     frame 1 (query) and second frame 2 (train), as std::pair<int,int> in the reference.
+ *   - there is NO CPU fallback: without a CUDA device vb_create fails with VB_ERR_CUDA.
+ */
+#ifndef VSLAM_B200_H
+#define VSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_OK 0
+#define VB_ERR_INVALID 1      /* bad argument (NULL, zero size where forbidden, min_items outside 1..8 ...) */
+#define VB_ERR_CUDA 2         /* a CUDA runtime call failed; see vb_last_error() */
+#define VB_ERR_TOO_FEW 3      /* fewer matches than min_items / fewer than 2 train descriptors (UB in the reference) */
+#define VB_ERR_CAPACITY 4     /* caller-provided output capacity too small; required size is reported */
+#define VB_ERR_NO_MODEL 5     /* RANSAC accepted no hypothesis (reference leaves `fundamental` empty) */
+
+typedef struct vb_ctx vb_ctx;   /* one per GPU per host thread; owns a stream and grow-only workspaces */
+typedef struct vb_tree vb_tree; /* device-resident SoA k-d tree */
+
+int vb_version(void);
+const char *vb_last_error(void);
+
+int vb_create(int device, vb_ctx **out);
+int vb_destroy(vb_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
+int vb_set_stream(vb_ctx *ctx, void *cuda_stream);
+int vb_synchronize(vb_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t vb_launch_count(const vb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * KD-tree over 2-D keypoints. Replaces construct_kdtree / nearest / radius_search.
+ * The tree is an implicit balanced tree stored in DFS pre-order (the reference's node-array order,
+ * src/KDTree.cpp:16): slot s with subtree length len has its left child at s+1 (len/2 points) and its
+ * right child at s+1+len/2 (len-len/2-1 points). Node arrays are SoA in HBM: x[], y[], idx[].
+ * Ties on the split coordinate are ordered by original index (std::nth_element leaves them
+ * unspecified), so the layout equals the reference's whenever split coordinates are distinct.
+ * ---------------------------------------------------------------------------------------------- */
+int vb_kdtree_build(vb_ctx *ctx, const float *pts_xy, uint32_t n, vb_tree **out);
+int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_xy_d, uint32_t n, vb_tree **out);
+int vb_kdtree_free(vb_tree *tree);
+uint32_t vb_kdtree_size(const vb_tree *tree);
+uint32_t vb_kdtree_height(const vb_tree *tree); /* floor(log2 n)+1, src/KDTree.cpp:33 */
+/* Pre-order export (either output may be NULL): idx_preorder[n] = original index of the point at each
+ * slot (frame_kdtree::KDTreeNode::pt_index), pts_preorder[n*2] = its coordinates (KDTree::KDTreeNode::pt). */
+int vb_kdtree_export(vb_tree *tree, uint32_t *idx_preorder, float *pts_preorder);
+/* Exact 1-NN for nq queries, same visiting order as the reference (near child, node, far child iff
+ * split^2 < best), so equidistant ties resolve identically. Outputs (any may be NULL):
+ * out_pt[nq*2] point value ({0,0} if nothing is closer than max_d2, as src/KDTree.cpp:38-42),
+ * out_idx[nq] original point index or -1, out_d2[nq] squared distance (max_d2 if none). */
+int vb_kdtree_nearest(vb_tree *tree, const float *q_xy, uint32_t nq, float max_d2, float *out_pt,
+                      int32_t *out_idx, float *out_d2);
+int vb_kdtree_nearest_d(vb_tree *tree, const float *q_xy_d, uint32_t nq, float max_d2, float *out_pt_d,
+                        int32_t *out_idx_d, float *out_d2_d);
+/* Radius search for nq queries: all points with dist^2 < r^2 (strict, :91) in DFS pre-order, as CSR.
+ * out_offsets[nq+1]; out_idx[cap] original indices. *out_total receives the total hit count; if it
+ * exceeds cap the call returns VB_ERR_CAPACITY after filling out_offsets (retry with a larger buffer). */
+int vb_kdtree_radius(vb_tree *tree, const float *q_xy, uint32_t nq, float radius, uint32_t *out_offsets,
+                     uint32_t *out_idx, uint64_t cap, uint64_t *out_total);
+int vb_kdtree_radius_d(vb_tree *tree, const float *q_xy_d, uint32_t nq, float radius, uint32_t *out_offsets_d,
+                       uint32_t *out_idx_d, uint64_t cap, uint64_t *out_total /* host */);
+
+/* ------------------------------------------------------------------------------------------------
+ * Descriptor matching. Replaces BFMatcher(NORM_HAMMING).knnMatch(k=2) + Lowe ratio (src/Frame.cpp:83-95).
+ * ---------------------------------------------------------------------------------------------- */
+/* Two nearest train descriptors per query; ties go to the lower train index. idx/dist are [n1][2].
+ * bytes must be a multiple of 4 and <= 64 (ORB: 32). Requires n2 >= 2. */
+int vb_knn2_hamming(vb_ctx *ctx, const uint8_t *d1, uint32_t n1, const uint8_t *d2, uint32_t n2, uint32_t bytes,
+                    int32_t *idx, int32_t *dist);
+/* knn2 + ratio test `(double)d0 < (double)d1 * ratio` (:91); survivors in query order.
+ * out_pairs has room for n1 pairs; *out_m receives the count. */
+int vb_match_hamming(vb_ctx *ctx, const uint8_t *d1, uint32_t n1, const uint8_t *d2, uint32_t n2, uint32_t bytes,
+                     double ratio, int32_t *out_pairs, uint32_t *out_m);
+/* Float descriptors (BASELINE config 3; not in the reference, which is Hamming-only at :83). */
+int vb_knn2_l2f(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, uint32_t n2, uint32_t dim, int32_t *idx,
+                float *dist);
+int vb_match_l2f(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, uint32_t n2, uint32_t dim, double ratio,
+                 int32_t *out_pairs, uint32_t *out_m);
+
+/* ------------------------------------------------------------------------------------------------
+ * RansacFilter. Replaces find_fundamental and its helpers (src/RansacFilter.cpp:36-67).
+ * seed is the value the reference would have obtained from std::random_device at :15 — the same seed
+ * gives the same std::mt19937 stream, hence the same sample sets.
+ * ---------------------------------------------------------------------------------------------- */
+/* Outputs: F[9] row-major (x2^T F x1 = 0), inlier_mask[m] (0/1), *n_inliers, *score (the (float)cv::sum
+ * of the winner's residuals), *best_hyp (index of the winning hypothesis). Optional outputs may be NULL.
+ * Returns VB_ERR_TOO_FEW if m < min_items, VB_ERR_NO_MODEL if no hypothesis beat the initial
+ * (0 inliers, score 0) best — in both cases nothing is written except *best_hyp = -1. */
+int vb_ransac_fundamental(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,
+                          const int32_t *matches, uint32_t m, int min_items, uint32_t max_iterations, float threshold,
+                          uint32_t seed, float *F, uint8_t *inlier_mask, int32_t *n_inliers, float *score,
+                          int32_t *best_hyp);
+/* Per-hypothesis view of the same run, for parity tests: sets[iters][8], F_all[iters][9],
+ * n_inliers[iters], score[iters]. Any output may be NULL. */
+int vb_ransac_hypotheses(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,
+                         const int32_t *matches, uint32_t m, int min_items, uint32_t max_iterations, float threshold,
+                         uint32_t seed, int32_t *sets, float *F_all, int32_t *n_inliers, float *score);
+/* Scoring only (compute_fundamental_residual, :105-140, for h models at once): corr[m][4] rows
+ * (x1,y1,x2,y2); F[h][9]; outputs n_inliers[h], score[h]. The BASELINE "hypotheses scored/s" entry. */
+int vb_ransac_score(vb_ctx *ctx, const float *corr, uint32_t m, const float *F, uint32_t h, float threshold,
+                    int32_t *n_inliers, float *score);
+int vb_ransac_score_d(vb_ctx *ctx, const float *corr_d, uint32_t m, const float *F_d, uint32_t h, float threshold,
+                      int32_t *n_inliers_d, float *score_d);
+/* The 8-point solve alone (compute_fundamental, :69-103) for h minimal samples: p1set/p2set [h][8][2]. */
+int vb_ransac_solve8(vb_ctx *ctx, const float *p1set, const float *p2set, uint32_t h, float *F);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole pair(s): match_features (src/Frame.cpp:82-105) = knn2 + ratio + find_fundamental + inlier
+ * copy-out, with everything between the input upload and the result download kept on the device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    double ratio;            /* 0.7 at src/Frame.cpp:91 */
+    int32_t min_items;       /* 8   at src/vslam.cpp:19 */
+    uint32_t max_iterations; /* 100 at src/vslam.cpp:19; 1024 in BASELINE config 2 */
+    float threshold;         /* 10  at src/vslam.cpp:19 */
+    uint32_t seed0;          /* pair i uses seed0 + i */
+} vb_pair_params;
+
+typedef struct {
+    int32_t status;      /* VB_OK, VB_ERR_TOO_FEW or VB_ERR_NO_MODEL for this pair */
+    int32_t n_tentative; /* matches surviving the ratio test */
+    int32_t n_matches;   /* final (RANSAC inlier) matches written for this pair */
+    int32_t best_hyp;
+    int32_t n_inliers;
+    float score;
+    float F[9];
+} vb_pair_result;
+
+/* One pair. out_matches has room for n1 pairs. */
+int vb_match_features(vb_ctx *ctx, const float *p1_xy, const uint8_t *d1, uint32_t n1, const float *p2_xy,
+                      const uint8_t *d2, uint32_t n2, uint32_t bytes, const vb_pair_params *params,
+                      int32_t *out_matches, vb_pair_result *result);
+/* A sequence: frames [nframes][k] keypoints, pair i = (frame i, frame i+1), i in [0, nframes-1).
+ * pts [nframes][k][2], desc [nframes][k][bytes]; results [nframes-1]; out_matches [nframes-1][k][2]
+ * (may be NULL to skip the match download). All pairs run in a handful of batched launches. */
+int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                 const vb_pair_params *params, vb_pair_result *results, int32_t *out_matches);
+int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint32_t nframes, uint32_t k,
+                   uint32_t bytes, const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Timing hook for bench.py: CUDA-event time (ms) of the kernels of one class recorded on the context's
+ * stream during the last call, keyed by name ("score", "hamming", "solve", ...). Returns <0 if unknown.
+ * ---------------------------------------------------------------------------------------------- */
+int vb_profile_enable(vb_ctx *ctx, int on);
+float vb_profile_last_ms(vb_ctx *ctx, const char *kernel_class);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSLAM_B200_H */

@@ -1,0 +1,408 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs. Bit-exact for indices, masks, counts, scores and F (the solve is a fully specified op
+sequence on both sides); the documented tolerance for F against anything else is 1e-5 relative
+Frobenius after sign/norm normalisation (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from vslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from vslam_b200.lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def rel_frob(a, b):
+    a, b = a.reshape(-1).astype(np.float64), b.reshape(-1).astype(np.float64)
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    return min(np.linalg.norm(a - b), np.linalg.norm(a + b))
+
+
+# ---------------------------------------------------------------- 8-point solve
+def test_solve8_bit_exact(ctx, oracle):
+    fp = synth.frame_pair(800, 21)
+    rng = np.random.default_rng(0)
+    gt = fp["gt"]
+    keep = np.nonzero(gt >= 0)[0]
+    H = 500
+    sel = np.stack([rng.choice(keep, 8, replace=False) for _ in range(H)])
+    p1s, p2s = fp["p1"][sel], fp["p2"][gt[sel]]
+    # degenerate sets too: repeated point, collinear points, all-zero
+    p1s[0] = p1s[0, 0]; p2s[0] = p2s[0, 0]
+    p1s[1, :, 1] = 100.0; p2s[1, :, 1] = 100.0
+    p1s[2] = 0; p2s[2] = 0
+    F = ctx.ransac_solve8(p1s, p2s)
+    for h in range(H):
+        Fo = oracle.compute_fundamental(p1s[h], p2s[h])
+        assert np.array_equal(bits(F[h]), bits(Fo)), h
+        if h > 2:
+            assert rel_frob(F[h], Fo) <= 1e-5
+
+
+def test_solve8_golden_inputs(ctx, oracle, golden):
+    F = ctx.ransac_solve8(golden["fm_p1"], golden["fm_p2"])
+    for h in range(len(F)):
+        assert np.array_equal(bits(F[h]), bits(oracle.compute_fundamental(golden["fm_p1"][h], golden["fm_p2"][h])))
+        assert rel_frob(F[h], golden["fm_F2"][h]) < 5e-3      # cv2's fp32 SVD is the noisy side
+
+
+# ---------------------------------------------------------------- scoring kernel
+def _oracle_scores(oracle, corr, Fs, thr):
+    m = len(corr)
+    p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+    matches = np.stack([np.arange(m), np.arange(m)], 1).astype(np.int32)
+    cnt, sc = [], []
+    for F in Fs:
+        _, _, n, s = oracle.residual(p1, p2, matches, F, thr)
+        cnt.append(n); sc.append(s)
+    return np.array(cnt, np.int32), np.array(sc, np.float32)
+
+
+def _hyp_bank(oracle, corr, H, seed):
+    rng = np.random.default_rng(seed)
+    Fs = np.zeros((H, 9), np.float32)
+    for h in range(H):
+        sel = rng.choice(len(corr), 8, replace=len(corr) < 8)
+        Fs[h] = oracle.compute_fundamental(corr[sel, :2], corr[sel, 2:]).reshape(-1)
+    return Fs
+
+
+@pytest.mark.parametrize("m", [1, 7, 127, 128, 129, 1000, 8191, 8192, 8193, 20000])
+def test_score_bit_exact_sizes(ctx, oracle, m):
+    corr = synth.correspondences(max(m, 8), m)[:m].copy()
+    H = 70
+    Fs = _hyp_bank(oracle, synth.correspondences(64, 1), H, m)
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    ocnt, osc = _oracle_scores(oracle, corr, Fs, 10.0)
+    assert np.array_equal(cnt, ocnt)
+    assert np.array_equal(bits(sc), bits(osc))
+
+
+@pytest.mark.parametrize("H", [1, 127, 129, 257, 600])
+def test_score_bit_exact_hypothesis_counts(ctx, oracle, H):
+    corr = synth.correspondences(3000, 5)
+    Fs = _hyp_bank(oracle, corr, H, H)
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    ocnt, osc = _oracle_scores(oracle, corr, Fs, 10.0)
+    assert np.array_equal(cnt, ocnt) and np.array_equal(bits(sc), bits(osc))
+    assert cnt.max() > 100     # realistic hypotheses, not all-outlier noise
+
+
+def test_score_golden_and_special_values(ctx, oracle, golden):
+    g = golden
+    p1, p2, mm = g["res_p1"], g["res_p2"], g["res_matches"]
+    corr = np.ascontiguousarray(np.concatenate([p1[mm[:, 0]], p2[mm[:, 1]]], 1), np.float32)
+    cnt, sc = ctx.ransac_score(corr, g["res_F"].reshape(-1, 9), float(g["res_thr"]))
+    assert np.array_equal(cnt, g["res_cnt"])                       # cv2-generated counts
+    for i in range(len(cnt)):
+        _, _, n, s = oracle.residual(p1, p2, mm, g["res_F"][i], float(g["res_thr"]))
+        assert cnt[i] == n
+        assert bits(sc[i:i + 1])[0] == bits(np.array([s]))[0] or (np.isnan(sc[i]) and np.isnan(s))
+    assert np.isnan(sc).any() and np.isinf(sc).any()
+
+
+def test_score_large_grouped_path(ctx, oracle):
+    """m large enough that the kernel folds whole 64-chunk groups inside a CTA."""
+    m, H = 300000, 1024
+    corr = synth.correspondences(m, 77)
+    Fs = _hyp_bank(oracle, corr[:5000], H, 3)
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    pick = np.r_[0:8, H - 8:H, 500:508]
+    ocnt, osc = _oracle_scores(oracle, corr, Fs[pick], 10.0)
+    assert np.array_equal(cnt[pick], ocnt) and np.array_equal(bits(sc[pick]), bits(osc))
+
+
+def test_score_linearity_property_full_size(ctx, oracle):
+    """Size-independent property at BASELINE size (1M matches): inlier counts are additive over any split
+    of the match set, and permuting hypotheses permutes the outputs."""
+    m, H = 1000000, 256
+    corr = synth.correspondences(m, 5)
+    Fs = _hyp_bank(oracle, corr[:4000], H, 9)
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    cut = 333333
+    c1, _ = ctx.ransac_score(corr[:cut].copy(), Fs, 10.0)
+    c2, _ = ctx.ransac_score(corr[cut:].copy(), Fs, 10.0)
+    assert np.array_equal(cnt, c1 + c2)
+    perm = np.random.default_rng(0).permutation(H)
+    cp, sp = ctx.ransac_score(corr, Fs[perm], 10.0)
+    assert np.array_equal(cp, cnt[perm]) and np.array_equal(bits(sp), bits(sc[perm]))
+    ocnt, osc = _oracle_scores(oracle, corr, Fs[:3], 10.0)
+    assert np.array_equal(cnt[:3], ocnt) and np.array_equal(bits(sc[:3]), bits(osc))
+
+
+# ---------------------------------------------------------------- sampling + full RANSAC
+@pytest.mark.parametrize("n,mi,iters,seed", [(8, 8, 50, 1), (9, 8, 64, 2), (100, 8, 100, 42), (3000, 8, 1024, 7),
+                                             (20, 5, 30, 9), (50, 1, 10, 3), (5000, 8, 4096, 11)])
+def test_sample_sets_bit_exact(ctx, oracle, n, mi, iters, seed):
+    corr = synth.correspondences(n, seed)
+    p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+    matches = np.stack([np.arange(n), np.arange(n)], 1).astype(np.int32)
+    g = ctx.ransac_hypotheses(p1, p2, matches, mi, iters, 10.0, seed)
+    assert np.array_equal(g["sets"], oracle.initialize_sets(n, mi, iters, seed))
+
+
+def test_sample_sets_with_rejections(ctx, oracle):
+    """~1M matches: libstdc++'s Lemire rejection fires about twice per 8192 draws; the kernel must replay it."""
+    n, iters, seed = 1000000, 2048, 123
+    corr = synth.correspondences(n, 3)
+    p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+    matches = np.stack([np.arange(n), np.arange(n)], 1).astype(np.int32)
+    g = ctx.ransac_hypotheses(p1, p2, matches, 8, iters, 10.0, seed)
+    o = oracle.initialize_sets(n, 8, iters, seed)
+    assert np.array_equal(g["sets"], o)
+
+    # the no-rejection replay of the raw stream would have differed (so the branch was exercised)
+    class MT(C.Structure):
+        _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int)]
+    st = MT()
+    oracle.lib.vbo_mt_seed(C.byref(st), seed)
+    oracle.lib.vbo_mt_next.restype = C.c_uint32
+    rej = 0
+    for i in range(iters * 8):
+        rng_ = n - (i % 8)
+        low = (oracle.lib.vbo_mt_next(C.byref(st)) * rng_) & 0xFFFFFFFF
+        rej += low < rng_ and low < ((1 << 32) - rng_) % rng_
+    assert rej > 0
+
+
+@pytest.mark.parametrize("k,iters,thr,seed", [(400, 100, 10.0, 5), (2000, 100, 10.0, 0), (2000, 1024, 10.0, 1),
+                                              (300, 64, 0.2, 3), (5000, 1024, 10.0, 2)])
+def test_find_fundamental_bit_exact(ctx, oracle, k, iters, thr, seed):
+    fp = synth.frame_pair(k, seed)
+    tent = oracle.match_hamming(fp["d1"], fp["d2"])
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 8, iters, thr, seed + 100, want_all=True)
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent, 8, iters, thr, seed + 100)
+    h = ctx.ransac_hypotheses(fp["p1"], fp["p2"], tent, 8, iters, thr, seed + 100)
+    assert np.array_equal(h["sets"], o["sets"])
+    assert np.array_equal(bits(h["F_all"]), bits(o["F_all"]))
+    assert np.array_equal(h["cnt_all"], o["cnt_all"])
+    assert np.array_equal(bits(h["score_all"]), bits(o["score_all"]))
+    assert g["rc"] == 0 and g["best"] == o["best"]
+    assert np.array_equal(bits(g["F"]), bits(o["F"]))
+    assert rel_frob(g["F"], o["F"]) <= 1e-5
+    assert np.array_equal(g["mask"], o["mask"])
+    assert g["n_inliers"] == o["n_inliers"] and bits(np.array([g["score"]]))[0] == bits(np.array([o["score"]]))[0]
+
+
+def test_find_fundamental_tie_rule(ctx, oracle):
+    fp = synth.frame_pair(300, 9, noise_px=0.0, outlier_frac=0.0)
+    tent = np.stack([np.arange(300), fp["gt"]], 1).astype(np.int32)
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 8, 256, 10.0, 77, want_all=True)
+    assert (o["cnt_all"] == o["cnt_all"].max()).sum() > 1
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent, 8, 256, 10.0, 77)
+    assert g["best"] == o["best"] and np.array_equal(g["mask"], o["mask"]) and np.array_equal(bits(g["F"]), bits(o["F"]))
+
+
+def test_find_fundamental_edge_cases(ctx, oracle):
+    fp = synth.frame_pair(100, 1)
+    tent = oracle.match_hamming(fp["d1"], fp["d2"])
+    # fewer matches than min_items: reference is UB; ABI reports TOO_FEW and writes nothing
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent[:5], 8, 10, 10.0, 1)
+    assert g["rc"] == 3 and g["best"] == -1 and not g["F"].any()
+    # exactly min_items matches
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent[:8], 8, 16, 10.0, 4)
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent[:8], 8, 16, 10.0, 4)
+    assert g["best"] == o["best"] and np.array_equal(g["mask"], o["mask"])
+    # min_items < 8: trailing sample slots stay 0 (src/RansacFilter.cpp:17)
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 5, 32, 10.0, 6, want_all=True)
+    h = ctx.ransac_hypotheses(fp["p1"], fp["p2"], tent, 5, 32, 10.0, 6)
+    assert np.array_equal(h["sets"], o["sets"]) and (h["sets"][:, 5:] == 0).all()
+    assert np.array_equal(bits(h["F_all"]), bits(o["F_all"]))
+    # threshold so small nothing is an inlier: winner decided by the score-only rule from (0, 0)
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 8, 32, 0.0, 2)
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent, 8, 32, 0.0, 2)
+    assert g["best"] == o["best"] and g["n_inliers"] == o["n_inliers"] and np.array_equal(g["mask"], o["mask"])
+    # all points identical: every residual is 0/0 = NaN, nothing is ever accepted
+    z1 = np.full((20, 2), 5.0, np.float32)
+    mm = np.stack([np.arange(20), np.arange(20)], 1).astype(np.int32)
+    o = oracle.find_fundamental(z1, z1, mm, 8, 16, 10.0, 2)
+    g = ctx.ransac_fundamental(z1, z1, mm, 8, 16, 10.0, 2)
+    assert (g["rc"] == 5) == (o["best"] < 0) and g["best"] == o["best"]
+
+
+# ---------------------------------------------------------------- Hamming matcher
+def test_knn2_hamming_golden(ctx, golden):
+    for name in ("knn", "knnc"):
+        idx, dist = ctx.knn2_hamming(golden[f"{name}_d1"], golden[f"{name}_d2"])
+        assert np.array_equal(idx, golden[f"{name}_idx"])                      # cv2 BFMatcher order
+        assert np.array_equal(dist.astype(np.float32), golden[f"{name}_dist"])
+        pairs = ctx.match_hamming(golden[f"{name}_d1"], golden[f"{name}_d2"], 0.7)
+        q = np.nonzero(golden[f"{name}_keep"])[0]
+        assert np.array_equal(pairs[:, 0], q) and np.array_equal(pairs[:, 1], golden[f"{name}_idx"][q, 0])
+
+
+@pytest.mark.parametrize("n1,n2,nbytes", [(1, 2, 32), (3, 5, 32), (255, 257, 32), (1000, 129, 32), (2000, 2000, 32),
+                                          (5000, 5000, 32), (700, 900, 16), (300, 400, 64)])
+def test_knn2_hamming_vs_oracle(ctx, oracle, n1, n2, nbytes):
+    rng = np.random.default_rng(n1 * 7 + n2)
+    d2 = synth.random_descriptors(rng, n2, nbytes)
+    d1 = synth.random_descriptors(rng, n1, nbytes)
+    k = min(n1, n2) // 2
+    d1[:k] = synth.flip_bits(rng, d2[rng.permutation(n2)[:k]], 12)
+    if n2 > 40:
+        d2[n2 - 20:] = d2[:20]         # duplicated train rows: equal distances, lower index must win
+    idx, dist = ctx.knn2_hamming(d1, d2)
+    oidx, odist = oracle.knn2_hamming(d1, d2)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
+    for ratio in (0.7, 0.9, 1.0):
+        assert np.array_equal(ctx.match_hamming(d1, d2, ratio), oracle.match_hamming(d1, d2, ratio))
+
+
+def test_hamming_too_few_train(ctx):
+    from vslam_b200.lib import VbError
+    d = np.zeros((4, 32), np.uint8)
+    with pytest.raises(VbError) as e:
+        ctx.knn2_hamming(d, d[:1])
+    assert e.value.code == 3
+
+
+# ---------------------------------------------------------------- whole pair / sequence
+@pytest.mark.parametrize("k,iters,seed", [(2000, 100, 0), (2000, 1024, 3), (5000, 1024, 1)])
+def test_match_features_bit_exact(ctx, oracle, k, iters, seed):
+    fp = synth.frame_pair(k, seed)
+    prm = ctx.params(0.7, 8, iters, 10.0, 1234 + seed)
+    g = ctx.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], prm)
+    o = oracle.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], 0.7, 8, iters, 10.0, 1234 + seed)
+    assert g["status"] == 0 and g["n_tentative"] == o["n_tentative"] and g["best"] == o["best"]
+    assert g["n"] == o["n"] and np.array_equal(g["matches"], o["matches"])
+    assert np.array_equal(bits(g["F"]), bits(o["F"])) and rel_frob(g["F"], o["F"]) <= 1e-5
+    assert o["n"] > 0.4 * k
+
+
+def test_pairs_run_sequence_bit_exact(ctx, oracle):
+    nframes, k = 9, 1500
+    pts, desc = synth.sequence(nframes, k, 42)
+    prm = ctx.params(0.7, 8, 256, 10.0, 500)
+    res, out = ctx.pairs_run(pts, desc, prm)
+    for i in range(nframes - 1):
+        o = oracle.match_features(pts[i], desc[i], pts[i + 1], desc[i + 1], 0.7, 8, 256, 10.0, 500 + i)
+        assert res["status"][i] == 0
+        assert res["n_tentative"][i] == o["n_tentative"] and res["best_hyp"][i] == o["best"]
+        assert res["n_matches"][i] == o["n"]
+        assert np.array_equal(out[i, :o["n"]], o["matches"])
+        assert np.array_equal(bits(res["F"][i]), bits(o["F"].reshape(-1)))
+    # no-download variant reports the same counts
+    res2, _ = ctx.pairs_run(pts, desc, prm, want_matches=False)
+    assert np.array_equal(res2["n_inliers"], res["n_inliers"]) and np.array_equal(res2["best_hyp"], res["best_hyp"])
+
+
+def test_pairs_run_degenerate_pair_in_batch(ctx, oracle):
+    """A pair whose descriptors do not match at all (< 8 tentative matches) must not disturb its neighbours."""
+    nframes, k = 5, 600
+    pts, desc = synth.sequence(nframes, k, 7)
+    desc[2] = synth.random_descriptors(np.random.default_rng(1), k)      # frame 2 unrelated to 1 and 3
+    prm = ctx.params(0.7, 8, 64, 10.0, 9)
+    res, out = ctx.pairs_run(pts, desc, prm)
+    for i in range(nframes - 1):
+        o = oracle.match_features(pts[i], desc[i], pts[i + 1], desc[i + 1], 0.7, 8, 64, 10.0, 9 + i)
+        if o["n"] < 0:
+            assert res["status"][i] == 3 and res["n_matches"][i] == 0
+        else:
+            assert res["status"][i] == 0 and res["n_matches"][i] == o["n"] and np.array_equal(out[i, :o["n"]], o["matches"])
+    assert (res["status"] == 3).any()
+
+
+# ---------------------------------------------------------------- KD-tree
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 100, 1023, 1024, 1025, 5000, 7000, 20000])
+def test_kdtree_build_bit_exact(ctx, oracle, n):
+    pts = synth.frame_pair(max(n, 8), n + 1)["p1"][:n].copy()
+    t = ctx.kdtree_build(pts)
+    idx, pre = t.export()
+    opre = oracle.kdtree_build(pts)
+    assert np.array_equal(idx.astype(np.int32), opre)
+    assert np.array_equal(pre, pts[opre])
+    assert t.height == oracle.lib.vbo_kdtree_height(n)
+    t.free()
+
+
+def test_kdtree_build_with_ties(ctx, oracle):
+    """Integer grid coordinates as in the reference's own test (tests/test_kdtree.cpp:39-45): massive ties.
+    The documented tie order (coordinate, then original index) must match the oracle's."""
+    rng = np.random.default_rng(0)
+    pts = rng.integers(0, 100, (2700, 2)).astype(np.float32)
+    t = ctx.kdtree_build(pts)
+    idx, _ = t.export()
+    assert np.array_equal(idx.astype(np.int32), oracle.kdtree_build(pts))
+    assert sorted(idx.tolist()) == list(range(2700))
+
+
+@pytest.mark.parametrize("n", [1, 5, 3000, 5000, 20000])
+def test_kdtree_queries_bit_exact(ctx, oracle, n):
+    rng = np.random.default_rng(n)
+    pts = synth.frame_pair(max(n, 8), n + 3)["p1"][:n].copy()
+    pre = oracle.kdtree_build(pts)
+    t = ctx.kdtree_build(pts)
+    nq = 600
+    q = np.ascontiguousarray(pts[rng.integers(0, n, nq)] + rng.uniform(-3, 3, (nq, 2)), np.float32)
+    q[:20] = pts[rng.integers(0, n, 20)]                       # exact hits
+    pt, idx, d2 = t.nearest(q)
+    for i in range(nq):
+        slot, od2 = oracle.kdtree_nearest(pts, pre, q[i])
+        assert idx[i] == pre[slot] and d2[i] == od2 and np.array_equal(pt[i], pts[pre[slot]])
+    pt0, idx0, _ = t.nearest(q[:50], 1e-12)                    # bounded search: mostly nothing in range
+    for i in range(50):
+        slot, _ = oracle.kdtree_nearest(pts, pre, q[i], 1e-12)
+        assert idx0[i] == (pre[slot] if slot >= 0 else -1)
+        if slot < 0:
+            assert np.array_equal(pt0[i], [0, 0])              # src/KDTree.cpp:38-42
+    for r in (2.0, 17.5, 60.0):
+        off, out = t.radius(q[:200], r)
+        for i in range(200):
+            oidx, c = oracle.kdtree_radius(pts, pre, q[i], r)
+            assert off[i + 1] - off[i] == c
+            assert np.array_equal(out[off[i]:off[i + 1]].astype(np.int32), oidx)     # same order (pre-order)
+    t.free()
+
+
+def test_kdtree_reference_test_protocol(ctx):
+    """The reference's own acceptance test (tests/test_kdtree.cpp:47-146) replayed against the GPU tree:
+    integer points in [0,100)^2, nearest accepted on equal distance, radius results compared as sets."""
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n = int(rng.integers(2500, 3000))
+        pts = rng.integers(0, 100, (n, 2)).astype(np.float32)
+        t = ctx.kdtree_build(pts)
+        q = rng.integers(0, 100, (16, 2)).astype(np.float32)
+        pt, idx, d2 = t.nearest(q)
+        dd = ((pts[None, :, :] - q[:, None, :]) ** 2).sum(-1)
+        assert np.array_equal(d2, dd.min(1).astype(np.float32))
+        r = float(rng.uniform(10, 100))
+        off, out = t.radius(q, r)
+        for i in range(len(q)):
+            assert sorted(out[off[i]:off[i + 1]].tolist()) == np.nonzero(dd[i] < np.float32(r) * np.float32(r))[0].tolist()
+        t.free()
+
+
+def test_kdtree_radius_capacity_contract(ctx):
+    pts = synth.frame_pair(1000, 1)["p1"]
+    t = ctx.kdtree_build(pts)
+    q = np.ascontiguousarray(pts[:10])
+    off, out, tot = np.zeros(11, np.uint32), np.zeros(4, np.uint32), C.c_uint64()
+    rc = ctx.L.vb_kdtree_radius(t.h, q.ctypes.data_as(C.c_void_p), 10, 500.0, off.ctypes.data_as(C.c_void_p),
+                                out.ctypes.data_as(C.c_void_p), 4, C.byref(tot))
+    assert rc == 4 and tot.value > 4 and off[10] == tot.value
+    t.free()
+
+
+# ---------------------------------------------------------------- float descriptors (config 3)
+@pytest.mark.parametrize("n1,n2,dim", [(300, 500, 128), (1000, 1000, 128), (200, 333, 64)])
+def test_knn2_l2f_bit_exact(ctx, oracle, n1, n2, dim):
+    fp = synth.frame_pair_float(max(n1, n2), 4, dim=dim)
+    d1, d2 = np.ascontiguousarray(fp["d1"][:n1]), np.ascontiguousarray(fp["d2"][:n2])
+    d2[-5:] = d2[:5]
+    idx, dist = ctx.knn2_l2f(d1, d2)
+    oidx, odist = oracle.knn2_l2f(d1, d2)
+    assert np.array_equal(idx, oidx) and np.array_equal(bits(dist), bits(odist))
+    assert np.array_equal(ctx.match_l2f(d1, d2, 0.7), oracle.match_l2f(d1, d2, 0.7))

@@ -1,0 +1,591 @@
+// kdtree.cu — 2-D k-d tree over keypoints: device build, batched exact 1-NN, batched radius search.
+//
+// Replaces construct_kdtree / nearest / radius_search (reference src/KDTree.cpp:3-35, :37-71, :73-101,
+// :107-171; include/KDTree.h:13-80).
+//
+// Layout. The reference mallocs N pointer nodes and fills them in DFS pre-order (root[size++], :16), so
+// a node's left child is always the next slot and its right child follows the len/2 nodes of the left
+// subtree. That makes the pointers redundant: the tree here is three SoA arrays in HBM — x[], y[],
+// idx[] in pre-order — and a traversal carries (slot, len) instead of a pointer.
+//
+// Build (k_kd_build, one CTA per tree). The reference recursively nth_element's each segment around
+// position l + len/2 on alternating axes. Here both axis orders are sorted once (bitonic sort of
+// (orderable(coord) << 32 | index) keys), and the two index lists are kept segment-aligned: at a level
+// that splits on x, every segment's median is simply Lx[l + len/2], Lx needs no change, and Ly is
+// stably partitioned per segment into [left | median | right] with one block-wide scan. All segments
+// of a level are processed in the same passes, so the build is height x O(N) work with ~6 block
+// barriers per level and no recursion. Working arrays live in shared memory when 33*N bytes fit
+// (N <= ~6500, which covers the 5 000-keypoint configs) and in an HBM workspace otherwise.
+//
+// Queries (k_kd_nearest, k_kd_radius): one thread per query, explicit stack in shared memory laid out
+// [depth][thread] (bank-conflict free). The visiting order is exactly the reference's recursion, so
+// equidistant nearest-neighbour ties and the pre-order of radius results come out identical.
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int KD_BUILD_THREADS = 1024;
+constexpr int KD_Q_THREADS = 128;
+constexpr int KD_MAX_DEPTH = 32;
+
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    f = __fadd_rn(f, 0.0f);   // -0 -> +0 so that the two zeros tie, as they do under operator<
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// in-place bitonic sort of npad (power of two) 64-bit keys by the whole CTA
+__device__ void bitonic_sort_u64(uint64_t *keys, uint32_t npad) {
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// sorts two key arrays with shared barriers (same stage structure)
+__device__ void bitonic_sort2_u64(uint64_t *ka, uint64_t *kb, uint32_t npad) {
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    uint64_t a = ka[i], b = ka[ixj];
+                    if ((a > b) == up) { ka[i] = b; ka[ixj] = a; }
+                    a = kb[i]; b = kb[ixj];
+                    if ((a > b) == up) { kb[i] = b; kb[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// exclusive block scan of packed (left, median) flag counts over positions [0, n); out[n] = total
+__device__ void block_scan_flags(const uint32_t *list, const uint8_t *side, const uint32_t *segL, const uint32_t *segR,
+                                 uint32_t n, uint64_t *out, uint64_t *warp_tot) {
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(threadIdx.x * per, n), e = min(b + per, n);
+    uint64_t local = 0;
+    for (uint32_t p = b; p < e; p++) {
+        if (segR[p] > segL[p]) {
+            const uint8_t s = side[list[p]];
+            local += (s == 0 ? 1ull : 0ull) + (s == 1 ? (1ull << 32) : 0ull);
+        }
+    }
+    uint64_t incl = local;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    uint64_t woff = 0;
+    for (int i = 0; i < w; i++) woff += warp_tot[i];
+    uint64_t run = woff + incl - local;
+    for (uint32_t p = b; p < e; p++) {
+        out[p] = run;
+        if (segR[p] > segL[p]) {
+            const uint8_t s = side[list[p]];
+            run += (s == 0 ? 1ull : 0ull) + (s == 1 ? (1ull << 32) : 0ull);
+        }
+    }
+    __syncthreads();
+}
+
+struct KdBuildArgs {
+    const float2 *pts;       // [ntrees][pts_stride]
+    size_t pts_stride;
+    uint32_t n, npad;
+    float *out_x, *out_y;    // [ntrees][n] pre-order
+    uint32_t *out_idx;
+    size_t out_stride;
+    uint8_t *ws;             // global workspace, ws_stride bytes per tree (lists; and keys when keys_global)
+    size_t ws_stride;
+    int lists_in_smem;       // working arrays in dynamic shared memory
+    int keys_mode;           // 0: both key arrays in smem, 1: one at a time in smem, 2: global
+};
+
+__global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint64_t warp_tot[KD_BUILD_THREADS / 32];
+    const uint32_t n = a.n, npad = a.npad, tid = threadIdx.x;
+    const float2 *pts = a.pts + (size_t)blockIdx.x * a.pts_stride;
+    uint8_t *gws = a.ws ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr;
+
+    // ---- carve the working arrays -----------------------------------------------------------
+    uint8_t *base = a.lists_in_smem ? smem : gws;
+    uint64_t *scan = reinterpret_cast<uint64_t *>(base);                  // [n+1]
+    uint32_t *L0 = reinterpret_cast<uint32_t *>(scan + (n + 1));          // three list buffers
+    uint32_t *L1 = L0 + n;
+    uint32_t *L2 = L1 + n;
+    uint32_t *segL = L2 + n;
+    uint32_t *segR = segL + n;
+    uint32_t *segB = segR + n;                                            // pre-order base of the segment
+    uint8_t *side = reinterpret_cast<uint8_t *>(segB + n);
+    const size_t lists_bytes = (size_t)(n + 1) * 8 + (size_t)n * 24 + ((n + 7) / 8) * 8;
+
+    // ---- sort both axis orders ---------------------------------------------------------------
+    uint32_t *Lx = L0, *Ly = L1, *spare = L2;
+    if (a.keys_mode == 0) {
+        // keys alias the (not yet used) working arrays in shared memory
+        uint64_t *kx = reinterpret_cast<uint64_t *>(smem), *ky = kx + npad;
+        for (uint32_t i = tid; i < npad; i += blockDim.x) {
+            uint64_t vx = ~0ull, vy = ~0ull;
+            if (i < n) {
+                const float2 p = pts[i];
+                vx = ((uint64_t)float_orderable(p.x) << 32) | i;
+                vy = ((uint64_t)float_orderable(p.y) << 32) | i;
+            }
+            kx[i] = vx; ky[i] = vy;
+        }
+        __syncthreads();
+        bitonic_sort2_u64(kx, ky, npad);
+        // move out through registers (n <= 8 * blockDim in this mode) because the lists alias the keys
+        uint32_t rx[8], ry[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t i = tid + r * blockDim.x;
+            rx[r] = (i < n) ? (uint32_t)kx[i] : 0;
+            ry[r] = (i < n) ? (uint32_t)ky[i] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t i = tid + r * blockDim.x;
+            if (i < n) { Lx[i] = rx[r]; Ly[i] = ry[r]; }
+        }
+    } else {
+        uint64_t *keys = (a.keys_mode == 1) ? reinterpret_cast<uint64_t *>(smem)
+                                            : reinterpret_cast<uint64_t *>(gws + ((lists_bytes + 15) / 16) * 16);
+        for (int axis = 0; axis < 2; axis++) {
+            for (uint32_t i = tid; i < npad; i += blockDim.x) {
+                uint64_t v = ~0ull;
+                if (i < n) {
+                    const float2 p = pts[i];
+                    v = ((uint64_t)float_orderable(axis ? p.y : p.x) << 32) | i;
+                }
+                keys[i] = v;
+            }
+            __syncthreads();
+            bitonic_sort_u64(keys, npad);
+            uint32_t *dst = axis ? Ly : Lx;   // lists are global in this mode: no aliasing with smem keys
+            for (uint32_t i = tid; i < n; i += blockDim.x) dst[i] = (uint32_t)keys[i];
+            __syncthreads();
+        }
+    }
+    for (uint32_t p = tid; p < n; p += blockDim.x) { segL[p] = 0; segR[p] = n; segB[p] = 0; }
+    __syncthreads();
+
+    float *ox = a.out_x + (size_t)blockIdx.x * a.out_stride;
+    float *oy = a.out_y + (size_t)blockIdx.x * a.out_stride;
+    uint32_t *oi = a.out_idx + (size_t)blockIdx.x * a.out_stride;
+
+    // ---- one pass per tree level ---------------------------------------------------------------
+    uint32_t height = 0;
+    for (uint32_t t = n; t > 0; t >>= 1) height++;
+    for (uint32_t level = 0; level < height; level++) {
+        uint32_t *A = (level & 1) ? Ly : Lx;    // list sorted along this level's axis
+        uint32_t *Bl = (level & 1) ? Lx : Ly;   // the other list, to be partitioned
+        // pass 1: classify every point of every live segment; medians become tree nodes
+        for (uint32_t p = tid; p < n; p += blockDim.x) {
+            const uint32_t l = segL[p], r = segR[p];
+            if (r > l) {
+                const uint32_t m = l + (r - l) / 2;   // src/KDTree.cpp:8
+                const uint32_t pt = A[p];
+                side[pt] = (p < m) ? 0 : (p == m) ? 1 : 2;
+                if (p == m) {
+                    const float2 v = pts[pt];
+                    const uint32_t slot = segB[p];
+                    ox[slot] = v.x; oy[slot] = v.y; oi[slot] = pt;
+                }
+            }
+        }
+        __syncthreads();
+        // pass 2: stable three-way partition of the other list, all segments at once
+        block_scan_flags(Bl, side, segL, segR, n, scan, warp_tot);
+        for (uint32_t p = tid; p < n; p += blockDim.x) {
+            const uint32_t l = segL[p], r = segR[p];
+            const uint32_t pt = Bl[p];
+            uint32_t np = p;
+            if (r > l) {
+                const uint32_t m = l + (r - l) / 2;
+                const uint64_t d = scan[p] - scan[l];
+                const uint32_t cl = (uint32_t)d, cm = (uint32_t)(d >> 32);
+                const uint8_t s = side[pt];
+                np = (s == 0) ? l + cl : (s == 1) ? m : m + 1 + (p - l - cl - cm);
+            }
+            spare[np] = pt;
+        }
+        __syncthreads();
+        // pass 3: shrink the segments
+        for (uint32_t p = tid; p < n; p += blockDim.x) {
+            const uint32_t l = segL[p], r = segR[p];
+            if (r > l) {
+                const uint32_t m = l + (r - l) / 2;
+                if (p < m) { segR[p] = m; segB[p] += 1; }
+                else if (p == m) { segL[p] = 0; segR[p] = 0; }
+                else { segL[p] = m + 1; segB[p] += (m - l) + 1; }
+            }
+        }
+        // rotate buffers: the partitioned copy becomes the current "other" list
+        if (level & 1) { uint32_t *t = Lx; Lx = spare; spare = t; }
+        else { uint32_t *t = Ly; Ly = spare; spare = t; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KD_Q_THREADS) k_kd_nearest(const float *__restrict__ tx, const float *__restrict__ ty,
+                                                             const uint32_t *__restrict__ tidx, uint32_t n,
+                                                             const float2 *__restrict__ q, uint32_t nq, float max_d2,
+                                                             float2 *__restrict__ out_pt, int32_t *__restrict__ out_idx,
+                                                             float *__restrict__ out_d2) {
+    __shared__ uint2 stack[KD_MAX_DEPTH][KD_Q_THREADS];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
+    if (i >= nq) return;
+    const float2 qp = q[i];
+    float best = max_d2;
+    int best_slot = -1;
+    int sp = 0;
+    // frame = (slot, len | axis << 30 | state << 31)
+    if (n > 0) stack[sp++][t] = make_uint2(0u, n);
+    while (sp > 0) {
+        const uint2 f = stack[sp - 1][t];
+        const uint32_t slot = f.x, len = f.y & 0x3fffffffu, axis = (f.y >> 30) & 1u, state = f.y >> 31;
+        const float x = __ldg(tx + slot), y = __ldg(ty + slot);
+        const float split = axis ? __fsub_rn(qp.y, y) : __fsub_rn(qp.x, x);   // :51
+        const uint32_t llen = len >> 1, rlen = len - llen - 1;
+        const bool go_left = split < 0.0f;                                    // :54
+        if (state == 0) {
+            stack[sp - 1][t].y = f.y | 0x80000000u;
+            const uint32_t cs = go_left ? slot + 1 : slot + 1 + llen, cl = go_left ? llen : rlen;
+            if (cl > 0) { stack[sp][t] = make_uint2(cs, cl | ((axis ^ 1u) << 30)); sp++; }
+        } else {
+            sp--;
+            const float dx = __fsub_rn(x, qp.x), dy = __fsub_rn(y, qp.y);     // :62-63
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (d2 < best) { best = d2; best_slot = (int)slot; }              // :64-67
+            const uint32_t cs = go_left ? slot + 1 + llen : slot + 1, cl = go_left ? rlen : llen;
+            if (cl > 0 && __fmul_rn(split, split) < best) {                   // :68-70
+                stack[sp][t] = make_uint2(cs, cl | ((axis ^ 1u) << 30));
+                sp++;
+            }
+        }
+    }
+    if (out_pt) out_pt[i] = best_slot >= 0 ? make_float2(tx[best_slot], ty[best_slot]) : make_float2(0.f, 0.f);
+    if (out_idx) out_idx[i] = best_slot >= 0 ? (int32_t)tidx[best_slot] : -1;
+    if (out_d2) out_d2[i] = best;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(KD_Q_THREADS) k_kd_radius(const float *__restrict__ tx, const float *__restrict__ ty,
+                                                            const uint32_t *__restrict__ tidx, uint32_t n,
+                                                            const float2 *__restrict__ q, uint32_t nq, float radius,
+                                                            uint32_t *__restrict__ counts,
+                                                            const uint32_t *__restrict__ offsets,
+                                                            uint32_t *__restrict__ out_idx) {
+    __shared__ uint2 stack[KD_MAX_DEPTH][KD_Q_THREADS];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
+    if (i >= nq) return;
+    const float2 qp = q[i];
+    const float r2 = __fmul_rn(radius, radius);   // SQ(radius), :74
+    uint32_t cnt = 0;
+    const uint32_t off = FILL ? offsets[i] : 0;
+    int sp = 0;
+    if (n > 0) stack[sp++][t] = make_uint2(0u, n);
+    while (sp > 0) {
+        const uint2 f = stack[--sp][t];
+        uint32_t slot = f.x, len = f.y & 0x3fffffffu, axis = (f.y >> 30) & 1u;
+        while (len > 0) {
+            const float x = __ldg(tx + slot), y = __ldg(ty + slot);
+            const float split = axis ? __fsub_rn(qp.y, y) : __fsub_rn(qp.x, x);
+            const uint32_t llen = len >> 1, rlen = len - llen - 1;
+            const float as = (split > 0.0f) ? split : -split;   // ABS macro, include/KDTree.h:10
+            if (as <= radius) {                                 // :88
+                const float dx = __fsub_rn(qp.x, x), dy = __fsub_rn(qp.y, y);
+                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                if (d2 < r2) {                                  // :91
+                    if (FILL) out_idx[off + cnt] = tidx[slot];
+                    cnt++;
+                }
+                if (rlen > 0) { stack[sp][t] = make_uint2(slot + 1 + llen, rlen | ((axis ^ 1u) << 30)); sp++; }
+                slot = slot + 1; len = llen;
+            } else if (split < 0.0f) {
+                slot = slot + 1; len = llen;
+            } else {
+                slot = slot + 1 + llen; len = rlen;
+            }
+            axis ^= 1u;
+        }
+    }
+    if (!FILL) counts[i] = cnt;
+}
+
+// single-CTA exclusive scan: out[0..n] (out[n] = total, also stored to *total as 64-bit)
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out,
+                                                   unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long wt[32];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(threadIdx.x * per, n), e = min(b + per, n);
+    unsigned long long local = 0;
+    for (uint32_t p = b; p < e; p++) local += in[p];
+    unsigned long long incl = local;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wt[w] = incl;
+    __syncthreads();
+    unsigned long long woff = 0, all = 0;
+    for (int i = 0; i < 32; i++) {
+        if (i < w) woff += wt[i];
+        all += wt[i];
+    }
+    unsigned long long run = woff + incl - local;
+    for (uint32_t p = b; p < e; p++) {
+        out[p] = (uint32_t)run;
+        run += in[p];
+    }
+    if (threadIdx.x == 0) {
+        out[n] = (uint32_t)all;
+        *total = all;
+    }
+}
+
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Builds ntrees trees of n points each. out arrays are [ntrees][out_stride].
+int kd_build_launch(vb_ctx *ctx, const float2 *pts_d, size_t pts_stride, uint32_t ntrees, uint32_t n, float *ox, float *oy,
+                    uint32_t *oi, size_t out_stride) {
+    if (n == 0 || ntrees == 0) return VB_OK;
+    KdBuildArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pts = pts_d; a.pts_stride = pts_stride; a.n = n; a.npad = next_pow2(n);
+    a.out_x = ox; a.out_y = oy; a.out_idx = oi; a.out_stride = out_stride;
+    const size_t lists_bytes = (size_t)(n + 1) * 8 + (size_t)n * 24 + ((n + 7) / 8) * 8;
+    const size_t keys2 = (size_t)a.npad * 16, keys1 = (size_t)a.npad * 8;
+    const size_t smem_max = 200 * 1024;
+    size_t smem = 0, ws_per_tree = 0;
+    if (lists_bytes <= smem_max && keys2 <= smem_max && n <= 8u * KD_BUILD_THREADS) {
+        a.lists_in_smem = 1; a.keys_mode = 0;
+        smem = lists_bytes > keys2 ? lists_bytes : keys2;
+    } else {
+        a.lists_in_smem = 0;
+        ws_per_tree = ((lists_bytes + 15) / 16) * 16;
+        if (keys1 <= smem_max) { a.keys_mode = 1; smem = keys1; }
+        else { a.keys_mode = 2; ws_per_tree += keys1; }
+    }
+    if (ws_per_tree) {
+        int rc = ctx->ws_ensure(WS_SCAN, ws_per_tree * ntrees);
+        if (rc) return rc;
+        a.ws = ctx->ws[WS_SCAN].as<uint8_t>();
+        a.ws_stride = ws_per_tree;
+    }
+    VB_CUDA(cudaFuncSetAttribute(k_kd_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    ctx->prof_begin("kd_build");
+    k_kd_build<<<ntrees, KD_BUILD_THREADS, smem, ctx->stream>>>(a);
+    ctx->prof_end("kd_build");
+    ctx->launches++;
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+static int tree_alloc(vb_ctx *ctx, uint32_t n, vb_tree **out) {
+    vb_tree *t = new vb_tree();
+    t->ctx = ctx; t->n = n;
+    uint32_t h = 0;
+    for (uint32_t v = n; v > 0; v >>= 1) h++;
+    t->height = h;   // floor(log2 n) + 1
+    if (n) {
+        cudaError_t e = cudaMallocAsync(&t->block, (size_t)n * 12, ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocAsync(%zu) -> %s", (size_t)n * 12, cudaGetErrorString(e));
+            delete t;
+            return VB_ERR_CUDA;
+        }
+        t->x = reinterpret_cast<float *>(t->block);
+        t->y = t->x + n;
+        t->idx = reinterpret_cast<uint32_t *>(t->y + n);
+    }
+    *out = t;
+    return VB_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_d, uint32_t n, vb_tree **out) {
+    VB_REQUIRE(ctx && out && (pts_d || n == 0), VB_ERR_INVALID, "NULL argument");
+    VB_REQUIRE(n < (1u << 30), VB_ERR_INVALID, "too many points");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tree *t = nullptr;
+    int rc = tree_alloc(ctx, n, &t);
+    if (rc) return rc;
+    rc = kd_build_launch(ctx, reinterpret_cast<const float2 *>(pts_d), 0, 1, n, t->x, t->y, t->idx, 0);
+    if (rc) { vb_kdtree_free(t); return rc; }
+    *out = t;
+    return VB_OK;
+}
+
+int vb_kdtree_build(vb_ctx *ctx, const float *pts, uint32_t n, vb_tree **out) {
+    VB_REQUIRE(ctx && out && (pts || n == 0), VB_ERR_INVALID, "NULL argument");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_PTS, (size_t)(n ? n : 1) * 8))) return rc;
+    if (n) VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_PTS].p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vb_kdtree_build_d(ctx, ctx->ws[WS_PTS].as<float>(), n, out))) return rc;
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may free or reuse pts immediately
+    return VB_OK;
+}
+
+int vb_kdtree_free(vb_tree *t) {
+    if (!t) return VB_OK;
+    if (t->block) {
+        cudaSetDevice(t->ctx->device);
+        cudaFreeAsync(t->block, t->ctx->stream);
+    }
+    delete t;
+    return VB_OK;
+}
+
+uint32_t vb_kdtree_size(const vb_tree *t) { return t ? t->n : 0; }
+uint32_t vb_kdtree_height(const vb_tree *t) { return t ? t->height : 0; }
+
+int vb_kdtree_export(vb_tree *t, uint32_t *idx_preorder, float *pts_preorder) {
+    VB_REQUIRE(t != nullptr, VB_ERR_INVALID, "tree is NULL");
+    if (t->n == 0) return VB_OK;
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<float> xs, ys;
+    if (pts_preorder) {
+        xs.resize(t->n); ys.resize(t->n);
+        VB_CUDA(cudaMemcpyAsync(xs.data(), t->x, (size_t)t->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VB_CUDA(cudaMemcpyAsync(ys.data(), t->y, (size_t)t->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (idx_preorder) VB_CUDA(cudaMemcpyAsync(idx_preorder, t->idx, (size_t)t->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pts_preorder)
+        for (uint32_t i = 0; i < t->n; i++) { pts_preorder[2 * i] = xs[i]; pts_preorder[2 * i + 1] = ys[i]; }
+    return VB_OK;
+}
+
+int vb_kdtree_nearest_d(vb_tree *t, const float *q_d, uint32_t nq, float max_d2, float *out_pt_d, int32_t *out_idx_d,
+                        float *out_d2_d) {
+    VB_REQUIRE(t && (q_d || nq == 0), VB_ERR_INVALID, "NULL argument");
+    if (nq == 0) return VB_OK;
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    ctx->prof_begin("kd_nearest");
+    k_kd_nearest<<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(
+        t->x, t->y, t->idx, t->n, reinterpret_cast<const float2 *>(q_d), nq, max_d2, reinterpret_cast<float2 *>(out_pt_d),
+        out_idx_d, out_d2_d);
+    ctx->prof_end("kd_nearest");
+    ctx->launches++;
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_kdtree_nearest(vb_tree *t, const float *q, uint32_t nq, float max_d2, float *out_pt, int32_t *out_idx, float *out_d2) {
+    VB_REQUIRE(t && (q || nq == 0), VB_ERR_INVALID, "NULL argument");
+    if (nq == 0) return VB_OK;
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_Q, (size_t)nq * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT0, (size_t)nq * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT1, (size_t)nq * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT2, (size_t)nq * 4))) return rc;
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_Q].p, q, (size_t)nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vb_kdtree_nearest_d(t, ctx->ws[WS_Q].as<float>(), nq, max_d2, ctx->ws[WS_OUT0].as<float>(),
+                                  ctx->ws[WS_OUT1].as<int32_t>(), ctx->ws[WS_OUT2].as<float>())))
+        return rc;
+    if (out_pt) VB_CUDA(cudaMemcpyAsync(out_pt, ctx->ws[WS_OUT0].p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_idx) VB_CUDA(cudaMemcpyAsync(out_idx, ctx->ws[WS_OUT1].p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_d2) VB_CUDA(cudaMemcpyAsync(out_d2, ctx->ws[WS_OUT2].p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VB_OK;
+}
+
+int vb_kdtree_radius_d(vb_tree *t, const float *q_d, uint32_t nq, float radius, uint32_t *out_offsets_d, uint32_t *out_idx_d,
+                       uint64_t cap, uint64_t *out_total) {
+    VB_REQUIRE(t && out_offsets_d && (q_d || nq == 0), VB_ERR_INVALID, "NULL argument");
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_OFFS, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_MISC, 64))) return rc;
+    uint32_t *counts = ctx->ws[WS_OFFS].as<uint32_t>();
+    unsigned long long *total_d = ctx->ws[WS_MISC].as<unsigned long long>();
+    const float2 *q2 = reinterpret_cast<const float2 *>(q_d);
+    ctx->prof_begin("kd_radius");
+    if (nq)
+        k_kd_radius<false><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q2, nq, radius,
+                                                                                      counts, nullptr, nullptr);
+    k_scan_u32<<<1, 1024, 0, ctx->stream>>>(counts, nq, out_offsets_d, total_d);
+    ctx->launches += nq ? 2 : 1;
+    VB_CUDA(cudaGetLastError());
+    unsigned long long total = 0;
+    VB_CUDA(cudaMemcpyAsync(&total, total_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_total) *out_total = total;
+    if (total > 0xffffffffull) { set_error("radius result too large for 32-bit CSR offsets"); return VB_ERR_CAPACITY; }
+    if (total > cap) {
+        ctx->prof_end("kd_radius");
+        set_error("radius search produced %llu hits, capacity %llu", total, (unsigned long long)cap);
+        return VB_ERR_CAPACITY;
+    }
+    if (total && nq) {
+        VB_REQUIRE(out_idx_d != nullptr, VB_ERR_INVALID, "out_idx is NULL");
+        k_kd_radius<true><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q2, nq, radius,
+                                                                                     nullptr, out_offsets_d, out_idx_d);
+        ctx->launches++;
+        VB_CUDA(cudaGetLastError());
+    }
+    ctx->prof_end("kd_radius");
+    return VB_OK;
+}
+
+int vb_kdtree_radius(vb_tree *t, const float *q, uint32_t nq, float radius, uint32_t *out_offsets, uint32_t *out_idx,
+                     uint64_t cap, uint64_t *out_total) {
+    VB_REQUIRE(t && out_offsets && (q || nq == 0), VB_ERR_INVALID, "NULL argument");
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_Q, (size_t)(nq ? nq : 1) * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT0, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT1, (size_t)(cap ? cap : 1) * 4))) return rc;
+    if (nq) VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_Q].p, q, (size_t)nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t total = 0;
+    rc = vb_kdtree_radius_d(t, ctx->ws[WS_Q].as<float>(), nq, radius, ctx->ws[WS_OUT0].as<uint32_t>(),
+                            ctx->ws[WS_OUT1].as<uint32_t>(), cap, &total);
+    if (out_total) *out_total = total;
+    if (rc != VB_OK && rc != VB_ERR_CAPACITY) return rc;
+    VB_CUDA(cudaMemcpyAsync(out_offsets, ctx->ws[WS_OUT0].p, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc == VB_OK && total && out_idx)
+        VB_CUDA(cudaMemcpyAsync(out_idx, ctx->ws[WS_OUT1].p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+}  // extern "C"

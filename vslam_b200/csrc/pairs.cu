@@ -1,0 +1,135 @@
+// pairs.cu — whole-pair pipeline: match_features (reference src/Frame.cpp:82-105) for one pair or for
+// every consecutive pair of a frame sequence, with all intermediates kept on the device.
+//
+// Per batch of P pairs the launch sequence is fixed (6 kernels, independent of P):
+//   k_knn2_partial -> k_knn2_finish (ratio test, ordered compaction, float4 correspondences, match count)
+//   -> k_sample_sets -> k_solve8 -> k_score -> k_select (best model, mask, inlier matches in order)
+// Pair i samples with std::mt19937(seed0 + i), i.e. what the reference would draw had
+// std::random_device returned seed0 + i for that frame.
+#include "common.cuh"
+#include "hamming_dev.cuh"
+#include "ransac_dev.cuh"
+
+namespace vb {
+
+constexpr uint32_t PAIRS_MAX_BATCH = 1024;
+
+static int pairs_core(vb_ctx *ctx, uint32_t P, const float2 *p1_base, const float2 *p2_base, size_t pts_stride,
+                      const uint32_t *d1_base, const uint32_t *d2_base, size_t desc_stride_words, uint32_t n1, uint32_t n2,
+                      uint32_t bytes, const vb_pair_params &prm, uint32_t seed0, vb_pair_result *results_d,
+                      int2 *out_matches_d) {
+    int rc;
+    HammingPlan hp;
+    if ((rc = hamming_plan(ctx, P, n1, n2, bytes, &hp))) return rc;
+    if ((rc = ctx->ws_ensure(WS_TENT, (size_t)P * n1 * sizeof(int2)))) return rc;
+    if ((rc = ctx->ws_ensure(WS_CORR, (size_t)P * n1 * sizeof(float4)))) return rc;
+    if ((rc = ctx->ws_ensure(WS_M, (size_t)P * sizeof(uint32_t)))) return rc;
+    KnnFinishArgs fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.ratio = prm.ratio;
+    fin.tent = ctx->ws[WS_TENT].as<int2>();
+    fin.mcap = n1;
+    fin.m_out = ctx->ws[WS_M].as<uint32_t>();
+    fin.corr = ctx->ws[WS_CORR].as<float4>();
+    fin.p1_base = p1_base;
+    fin.p2_base = p2_base;
+    fin.pts_stride = pts_stride;
+    if ((rc = hamming_launch(ctx, hp, d1_base, d2_base, desc_stride_words, fin))) return rc;
+    RansacPlan rp;
+    if ((rc = ransac_plan(ctx, P, n1, n1, prm.max_iterations, prm.min_items, &rp))) return rc;
+    ProblemDims dims{ctx->ws[WS_M].as<uint32_t>(), 0, seed0};
+    return ransac_run(ctx, rp, ctx->ws[WS_CORR].as<float4>(), dims, prm.threshold, results_d, nullptr,
+                      ctx->ws[WS_TENT].as<int2>(), out_matches_d);
+}
+
+static int check_params(const vb_pair_params *p, uint32_t bytes, uint32_t n2) {
+    VB_REQUIRE(p != nullptr, VB_ERR_INVALID, "params is NULL");
+    VB_REQUIRE(p->min_items >= 1 && p->min_items <= 8, VB_ERR_INVALID, "min_items must be in 1..8");
+    VB_REQUIRE(p->max_iterations > 0, VB_ERR_INVALID, "max_iterations is 0");
+    VB_REQUIRE(bytes == 16 || bytes == 32 || bytes == 64, VB_ERR_INVALID, "descriptor bytes must be 16, 32 or 64");
+    VB_REQUIRE(n2 >= 2, VB_ERR_TOO_FEW, "knnMatch(k=2) needs at least 2 train descriptors");
+    return VB_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint32_t nframes, uint32_t k, uint32_t bytes,
+                   const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d) {
+    VB_REQUIRE(ctx && pts_d && desc_d && results_d, VB_ERR_INVALID, "NULL argument");
+    int rc;
+    if ((rc = check_params(params, bytes, k))) return rc;
+    if (nframes < 2) return VB_OK;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t P = nframes - 1, W = bytes / 4;
+    const float2 *pts = reinterpret_cast<const float2 *>(pts_d);
+    const uint32_t *desc = reinterpret_cast<const uint32_t *>(desc_d);
+    for (uint32_t b0 = 0; b0 < P; b0 += PAIRS_MAX_BATCH) {
+        const uint32_t pb = (P - b0 < PAIRS_MAX_BATCH) ? P - b0 : PAIRS_MAX_BATCH;
+        rc = pairs_core(ctx, pb, pts + (size_t)b0 * k, pts + (size_t)(b0 + 1) * k, k, desc + (size_t)b0 * k * W,
+                        desc + (size_t)(b0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + b0,
+                        results_d + b0, out_matches_d ? reinterpret_cast<int2 *>(out_matches_d) + (size_t)b0 * k : nullptr);
+        if (rc) return rc;
+    }
+    return VB_OK;
+}
+
+int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                 const vb_pair_params *params, vb_pair_result *results, int32_t *out_matches) {
+    VB_REQUIRE(ctx && pts && desc && results, VB_ERR_INVALID, "NULL argument");
+    int rc;
+    if ((rc = check_params(params, bytes, k))) return rc;
+    if (nframes < 2) return VB_OK;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t P = nframes - 1;
+    const size_t pts_bytes = (size_t)nframes * k * 8, desc_bytes = (size_t)nframes * k * bytes;
+    if ((rc = ctx->ws_ensure(WS_PTS, pts_bytes))) return rc;
+    if ((rc = ctx->ws_ensure(WS_DESC, desc_bytes))) return rc;
+    if ((rc = ctx->ws_ensure(WS_RESULT, (size_t)P * sizeof(vb_pair_result)))) return rc;
+    if (out_matches && (rc = ctx->ws_ensure(WS_OUTMATCH, (size_t)P * k * 8))) return rc;
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_PTS].p, pts, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_DESC].p, desc, desc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vb_pairs_run_d(ctx, ctx->ws[WS_PTS].as<float>(), ctx->ws[WS_DESC].as<uint8_t>(), nframes, k, bytes, params,
+                             ctx->ws[WS_RESULT].as<vb_pair_result>(),
+                             out_matches ? ctx->ws[WS_OUTMATCH].as<int32_t>() : nullptr)))
+        return rc;
+    VB_CUDA(cudaMemcpyAsync(results, ctx->ws[WS_RESULT].p, (size_t)P * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    if (out_matches)
+        VB_CUDA(cudaMemcpyAsync(out_matches, ctx->ws[WS_OUTMATCH].p, (size_t)P * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VB_OK;
+}
+
+int vb_match_features(vb_ctx *ctx, const float *p1, const uint8_t *d1, uint32_t n1, const float *p2, const uint8_t *d2,
+                      uint32_t n2, uint32_t bytes, const vb_pair_params *params, int32_t *out_matches, vb_pair_result *result) {
+    VB_REQUIRE(ctx && p1 && d1 && p2 && d2 && result, VB_ERR_INVALID, "NULL argument");
+    int rc;
+    if ((rc = check_params(params, bytes, n2))) return rc;
+    VB_REQUIRE(n1 > 0, VB_ERR_TOO_FEW, "no query keypoints");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ctx->ws_ensure(WS_P1, (size_t)n1 * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_P2, (size_t)n2 * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_D1, (size_t)n1 * bytes))) return rc;
+    if ((rc = ctx->ws_ensure(WS_D2, (size_t)n2 * bytes))) return rc;
+    if ((rc = ctx->ws_ensure(WS_RESULT, sizeof(vb_pair_result)))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUTMATCH, (size_t)n1 * 8))) return rc;
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_P1].p, p1, (size_t)n1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_P2].p, p2, (size_t)n2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_D1].p, d1, (size_t)n1 * bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_D2].p, d2, (size_t)n2 * bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = pairs_core(ctx, 1, ctx->ws[WS_P1].as<float2>(), ctx->ws[WS_P2].as<float2>(), 0, ctx->ws[WS_D1].as<uint32_t>(),
+                         ctx->ws[WS_D2].as<uint32_t>(), 0, n1, n2, bytes, *params, params->seed0,
+                         ctx->ws[WS_RESULT].as<vb_pair_result>(), ctx->ws[WS_OUTMATCH].as<int2>())))
+        return rc;
+    VB_CUDA(cudaMemcpyAsync(result, ctx->ws[WS_RESULT].p, sizeof(vb_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_matches && result->n_matches > 0)
+        VB_CUDA(cudaMemcpy(out_matches, ctx->ws[WS_OUTMATCH].p, (size_t)result->n_matches * 8, cudaMemcpyDeviceToHost));
+    return VB_OK;
+}
+
+}  // extern "C"
