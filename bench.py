@@ -140,11 +140,11 @@ def run_reference(args, rank, world):
     sample = int(min(args.frames - 1, max(2 * cores, 8)))
     pts, desc = synth.sequence(sample + 1, args.kpts, 1000)
     for _ in range(args.warmup):
-        cpu_pairs_per_s(orc, pts, desc, min(sample, cores), args.hyps, args.threshold, 1)
+        cpu_pairs_per_s(orc, pts, desc, min(sample, cores), args.hyps, args.threshold, 1, threads=cores)
     t0 = time.perf_counter()
     used = 1
     for _ in range(args.steps):
-        _, used, _, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1)
+        _, used, _, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=cores)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -187,7 +187,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) stream: the ABI treats a NULL stream as "use the context's own stream", and
+    # torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     nframes, k, nbytes = args.frames, args.kpts, 32
@@ -310,7 +313,7 @@ def main():
         cores = os.cpu_count() or 1
         v1, _, dt1, _ = cpu_pairs_per_s(orc, pts, desc, 2, args.hyps, args.threshold, 1, threads=1)
         sample = int(min(P, max(cores, 8)))
-        vN, used, dtN, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=0)
+        vN, used, dtN, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=cores)
         # parity spot check of the timed GPU output against the same oracle (first pair)
         o = orc.match_features(pts[0], desc[0], pts[1], desc[1], 0.7, 8, args.hyps, args.threshold, 1)
         parity = bool(o["n"] == int(res["n_matches"][0]) and o["best"] == int(res["best_hyp"][0]))

@@ -23,9 +23,11 @@
 
 namespace vb {
 
+// Carry-save adder on three bit-planes, pinned to exactly two LOP3 (left to itself the compiler folds the
+// preceding XORs into the majority and ends up with ~27 LOP3 per 256-bit distance instead of 16).
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
-    sum = a ^ b ^ c;                       // LOP3 0x96
-    carry = (a & b) | (a & c) | (b & c);   // LOP3 0xE8
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));     // a ^ b ^ c
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));   // majority
 }
 
 // popcount of 8 words with 4 POPC: ones + 2*twos + 4*fours
@@ -118,14 +120,24 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint32_t *__
                 const uint4 v = *reinterpret_cast<const uint4 *>(tb + j * W + 4 * i);
                 b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
             }
+            uint32_t d[QPT];
+            bool upd = false;
 #pragma unroll
             for (int k = 0; k < QPT; k++) {
-                const uint32_t d = hamming_words<W>(a[k], b);
-                if (d < bd2[k]) {   // equal distance never displaces an earlier (lower) index
-                    const uint32_t jg = ts + j;
-                    if (d < bd1[k]) { bd2[k] = bd1[k]; bj2[k] = bj1[k]; bd1[k] = d; bj1[k] = jg; }
-                    else { bd2[k] = d; bj2[k] = jg; }
-                }
+                d[k] = hamming_words<W>(a[k], b);
+                upd |= d[k] < bd2[k];
+            }
+            // The top-2 update is rare after the first few hundred candidates (probability ~2/j at
+            // candidate j); one warp vote keeps it off the common path instead of ~10 predicated
+            // instructions per distance.
+            if (__any_sync(0xffffffffu, upd)) {
+                const uint32_t jg = ts + j;
+#pragma unroll
+                for (int k = 0; k < QPT; k++)
+                    if (d[k] < bd2[k]) {   // equal distance never displaces an earlier (lower) index
+                        if (d[k] < bd1[k]) { bd2[k] = bd1[k]; bj2[k] = bj1[k]; bd1[k] = d[k]; bj1[k] = jg; }
+                        else { bd2[k] = d[k]; bj2[k] = jg; }
+                    }
             }
         }
         __syncthreads();   // everyone is done with tile[buf] before it is refilled two iterations later
@@ -205,7 +217,9 @@ int hamming_plan(vb_ctx *ctx, uint32_t P, uint32_t n1, uint32_t n2, uint32_t byt
     pl->P = P; pl->n1 = n1; pl->n2 = n2; pl->W = bytes / 4;
     // two queries per thread once the grid is large anyway (halves the shared-memory reads per pair)
     const uint32_t qt1 = div_up(n1, KNN_THREADS);
-    pl->qpt = ((uint64_t)P * qt1 >= 8ull * ctx->sm_count) ? 2 : 1;
+    pl->qpt = ((uint64_t)P * qt1 >= 16ull * ctx->sm_count && pl->W <= 8) ? 4
+              : ((uint64_t)P * qt1 >= 8ull * ctx->sm_count) ? 2 : 1;
+    if (const char *e = getenv("VB_HAMMING_QPT")) pl->qpt = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 1;
     pl->qtiles = div_up(n1, KNN_THREADS * pl->qpt);
     // split the train set so that a small batch still fills the machine (~4 CTAs per SM)
     uint64_t want = 4ull * ctx->sm_count;
@@ -224,7 +238,10 @@ template <int W> static void launch_partial(vb_ctx *ctx, const HammingPlan &pl, 
                                             size_t stride_words) {
     dim3 grid(pl.qtiles, pl.nsplits, pl.P);
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
-    if (pl.qpt == 2)
+    if (pl.qpt == 4)
+        k_knn2_partial<W, 4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d1, d2, stride_words, pl.n1, pl.n2, pl.split_len,
+                                                                    pl.nsplits, part);
+    else if (pl.qpt == 2)
         k_knn2_partial<W, 2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d1, d2, stride_words, pl.n1, pl.n2, pl.split_len,
                                                                     pl.nsplits, part);
     else
