@@ -63,6 +63,10 @@ uint64_t vb_launch_count(const vb_ctx *ctx);
  * ---------------------------------------------------------------------------------------------- */
 int vb_kdtree_build(vb_ctx *ctx, const float *pts_xy, uint32_t n, vb_tree **out);
 int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_xy_d, uint32_t n, vb_tree **out);
+/* Re-create the device tree from a pre-order node array that already exists on the host (what the
+ * reference's KDTree::root / frame_kdtree::root hold): pts_preorder[n*2], idx_preorder[n] (NULL = slot
+ * numbers). Used by the C++ adapter when a caller hands it a tree it has no device copy of. */
+int vb_kdtree_import(vb_ctx *ctx, const float *pts_preorder, const uint32_t *idx_preorder, uint32_t n, vb_tree **out);
 int vb_kdtree_free(vb_tree *tree);
 uint32_t vb_kdtree_size(const vb_tree *tree);
 uint32_t vb_kdtree_height(const vb_tree *tree); /* floor(log2 n)+1, src/KDTree.cpp:33 */
@@ -120,6 +124,13 @@ int vb_ransac_fundamental(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const fl
 int vb_ransac_hypotheses(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,
                          const int32_t *matches, uint32_t m, int min_items, uint32_t max_iterations, float threshold,
                          uint32_t seed, int32_t *sets, float *F_all, int32_t *n_inliers, float *score);
+/* initialize_sets alone (:6-34): sets[iters][8] for n_matches candidates. */
+int vb_ransac_sample_sets(vb_ctx *ctx, uint32_t n_matches, int min_items, uint32_t max_iterations, uint32_t seed,
+                          int32_t *sets);
+/* compute_fundamental_residual for ONE model with its inlier mask (:105-140). */
+int vb_ransac_residual(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,
+                       const int32_t *matches, uint32_t m, const float *F, float threshold, uint8_t *inlier_mask,
+                       int32_t *n_inliers, float *score);
 /* Scoring only (compute_fundamental_residual, :105-140, for h models at once): corr[m][4] rows
  * (x1,y1,x2,y2); F[h][9]; outputs n_inliers[h], score[h]. The BASELINE "hypotheses scored/s" entry. */
 int vb_ransac_score(vb_ctx *ctx, const float *corr, uint32_t m, const float *F, uint32_t h, float threshold,

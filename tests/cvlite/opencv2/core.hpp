@@ -59,8 +59,13 @@ typedef Point2i Point;
 
 }  // namespace cv
 
+#if defined(CVLITE_WITH_ORACLE_HOOKS) && !defined(CVLITE_WITH_MAT)
+#define CVLITE_WITH_MAT
+#endif
+
 #ifdef CVLITE_WITH_MAT
-// ---- oracle hooks (C, oracle/vb_oracle.c) used by the Mat subset -------------------------------
+#ifdef CVLITE_WITH_ORACLE_HOOKS
+// ---- oracle hooks (C, oracle/vb_oracle.c) used by SVDecomp / sum / the seed stand-in -------------
 extern "C" {
 void vbo_null_vector_8x9(const float *A /*8x9 row-major*/, float *f9);
 void vbo_svd3x3(const float *F /*3x3*/, float *U /*3x3*/, float *D /*3*/, float *Vt /*3x3*/);
@@ -78,6 +83,7 @@ struct cvlite_seeded_random_device {
 };
 }  // namespace std
 #define random_device cvlite_seeded_random_device
+#endif  // CVLITE_WITH_ORACLE_HOOKS
 
 #define CV_32FC1 5
 #define CV_32F 5
@@ -188,6 +194,7 @@ inline void reduce(const Mat &src, Mat &dst, int /*dim = 0*/, int /*REDUCE_SUM*/
     }
     dst = r;
 }
+#ifdef CVLITE_WITH_ORACLE_HOOKS
 inline Scalar_ sum(const Mat &m) {
     Mat c = (m.rows == 1) ? m.clone() : m.reshape(0, 1);
     Scalar_ s;
@@ -217,6 +224,7 @@ inline void SVDecomp(const Mat &A, Mat &D, Mat &U, Mat &Vt, int /*flags*/) {
         std::abort();
     }
 }
+#endif  // CVLITE_WITH_ORACLE_HOOKS
 
 }  // namespace cv
 #endif  // CVLITE_WITH_MAT

@@ -459,6 +459,33 @@ int vb_kdtree_build(vb_ctx *ctx, const float *pts, uint32_t n, vb_tree **out) {
     return VB_OK;
 }
 
+int vb_kdtree_import(vb_ctx *ctx, const float *pts_preorder, const uint32_t *idx_preorder, uint32_t n, vb_tree **out) {
+    VB_REQUIRE(ctx && out && (pts_preorder || n == 0), VB_ERR_INVALID, "NULL argument");
+    VB_REQUIRE(n < (1u << 30), VB_ERR_INVALID, "too many points");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tree *t = nullptr;
+    int rc = tree_alloc(ctx, n, &t);
+    if (rc) return rc;
+    if (n) {
+        std::vector<float> soa((size_t)n * 3);
+        uint32_t *ii = reinterpret_cast<uint32_t *>(soa.data() + (size_t)n * 2);
+        for (uint32_t i = 0; i < n; i++) {
+            soa[i] = pts_preorder[2 * i];
+            soa[n + i] = pts_preorder[2 * i + 1];
+            ii[i] = idx_preorder ? idx_preorder[i] : i;
+        }
+        cudaError_t e = cudaMemcpyAsync(t->block, soa.data(), (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("vb_kdtree_import: %s", cudaGetErrorString(e));
+            vb_kdtree_free(t);
+            return VB_ERR_CUDA;
+        }
+    }
+    *out = t;
+    return VB_OK;
+}
+
 int vb_kdtree_free(vb_tree *t) {
     if (!t) return VB_OK;
     if (t->block) {

@@ -39,10 +39,10 @@ assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 60
 
 EXPORTS = [
     "vb_version", "vb_last_error", "vb_create", "vb_destroy", "vb_set_stream", "vb_synchronize", "vb_launch_count",
-    "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
+    "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
-    "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_solve8",
+    "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
     "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_profile_enable", "vb_profile_last_ms",
 ]
 
@@ -73,6 +73,7 @@ def load_library() -> C.CDLL:
     L.vb_launch_count.argtypes = [vp]
     L.vb_kdtree_build.argtypes = [vp, vp, u32, C.POINTER(vp)]
     L.vb_kdtree_build_d.argtypes = [vp, vp, u32, C.POINTER(vp)]
+    L.vb_kdtree_import.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
     L.vb_kdtree_free.argtypes = [vp]
     L.vb_kdtree_size.restype = u32
     L.vb_kdtree_size.argtypes = [vp]
@@ -93,6 +94,8 @@ def load_library() -> C.CDLL:
     L.vb_ransac_score.argtypes = [vp, vp, u32, vp, u32, f32, vp, vp]
     L.vb_ransac_score_d.argtypes = [vp, vp, u32, vp, u32, f32, vp, vp]
     L.vb_ransac_solve8.argtypes = [vp, vp, vp, u32, vp]
+    L.vb_ransac_sample_sets.argtypes = [vp, u32, C.c_int, u32, u32, vp]
+    L.vb_ransac_residual.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp, f32, vp, C.POINTER(i32), C.POINTER(f32)]
     L.vb_match_features.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, C.POINTER(PairResult)]
     L.vb_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
