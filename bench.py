@@ -333,6 +333,7 @@ def main():
                 "single_pair_match_features_ms": single_ms,
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
+        line["kdtree"] = kdtree_stage(ctx, torch, dev, pts, k)
         if args.sweep:
             line["score_sweep"] = score_sweep(ctx, torch, dev, peak)
         print(json.dumps(line), flush=True)
@@ -340,6 +341,54 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def kdtree_stage(ctx, torch, dev, pts, k):
+    """KD-tree rows of the path (not part of the pairs/s metric): one frame's tree build, k nearest queries and
+    k radius-2 queries (the search-by-projection radius, src/vslam.cpp:149) on the GPU, next to the reference's
+    own src/KDTree.cpp timed on one host core (oracle/_ref, when it travelled with the repo)."""
+    p = np.ascontiguousarray(pts[1])
+    rng = np.random.default_rng(0)
+    q = np.ascontiguousarray(p + rng.uniform(-2, 2, p.shape), np.float32)
+    p_d, q_d = torch.from_numpy(p).to(dev), torch.from_numpy(q).to(dev)
+    out_pt = torch.zeros((k, 2), dtype=torch.float32, device=dev)
+    out_idx = torch.zeros(k, dtype=torch.int32, device=dev)
+    out_d2 = torch.zeros(k, dtype=torch.float32, device=dev)
+    offs = torch.zeros(k + 1, dtype=torch.int32, device=dev)
+    hits = torch.zeros(16 * k, dtype=torch.int32, device=dev)
+    L = ctx.L
+    res = {}
+    tree = C.c_void_p()
+    tot = C.c_uint64()
+    ms = {"kd_build": [], "kd_nearest": [], "kd_radius": []}
+    for it in range(8):
+        ctx.profile(it >= 3)
+        if tree:
+            L.vb_kdtree_free(tree)
+        ctx._chk(L.vb_kdtree_build_d(ctx.h, p_d.data_ptr(), k, C.byref(tree)))
+        ctx._chk(L.vb_kdtree_nearest_d(tree, q_d.data_ptr(), k, float("inf"), out_pt.data_ptr(), out_idx.data_ptr(), out_d2.data_ptr()))
+        ctx._chk(L.vb_kdtree_radius_d(tree, q_d.data_ptr(), k, 2.0, offs.data_ptr(), hits.data_ptr(), 16 * k, C.byref(tot)))
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            for name in ms:
+                ms[name].append(ctx.profile_ms(name))
+    ctx.profile(False)
+    L.vb_kdtree_free(tree)
+    res["gpu_ms"] = {n: float(np.mean(v)) for n, v in ms.items()}
+    res["gpu_queries_per_s"] = {"nearest": k / (res["gpu_ms"]["kd_nearest"] * 1e-3), "radius2": k / (res["gpu_ms"]["kd_radius"] * 1e-3)}
+    res["radius2_hits"] = int(tot.value)
+    try:
+        from oracle_lib import Ref
+        if Ref.available():
+            R = Ref()
+            t = lambda which, reps: float(R.lib.vbref_kdtree_time_ms(which, p, k, q, k, 2.0, reps))
+            res["reference_cpu_ms_1core"] = {"build_value_tree": t(0, 20), "nearest_x_k": t(1, 10), "radius2_x_k": t(2, 10),
+                                             "build_frame_kdtree_as_written": t(3, 1), "radius2_frame_kdtree_x_k": t(4, 10)}
+            res["reference_note"] = ("reference src/KDTree.cpp compiled unmodified (oracle/_ref); frame_kdtree build is slow "
+                                     "as written because its comparator copies the point vector (src/KDTree.cpp:128)")
+    except Exception as e:  # the checker is optional here
+        res["reference_cpu_ms_1core"] = f"unavailable: {e}"
+    return res
 
 
 def score_sweep(ctx, torch, dev, peak):

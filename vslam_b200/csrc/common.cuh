@@ -104,6 +104,8 @@ struct vb_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of vb_pairs_run
+    std::vector<cudaEvent_t> events;                      // untimed events for the copy/compute pipeline
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];
     uint64_t launches = 0;

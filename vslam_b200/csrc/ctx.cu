@@ -63,6 +63,9 @@ int vb_destroy(vb_ctx *c) {
         if (kv.second.a) cudaEventDestroy(kv.second.a);
         if (kv.second.b) cudaEventDestroy(kv.second.b);
     }
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return VB_OK;

@@ -30,31 +30,40 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));   // majority
 }
 
-// popcount of 8 words with 4 POPC: ones + 2*twos + 4*fours
-__device__ __forceinline__ uint32_t popc8(const uint32_t (&x)[8]) {
-    uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
-    csa(x[0], x[1], x[2], s1, c1);
-    csa(x[3], x[4], x[5], s2, c2);
-    csa(s1, s2, x[6], s3, c3);
-    csa(c1, c2, c3, s4, c4);
-    return __popc(s3) + __popc(x[7]) + 2u * __popc(s4) + 4u * __popc(c4);
+// Integer multiply-add pinned to the FMA pipe: the multiplier is a run-time register (the kernel is handed
+// the constants 1, 2, 4 as launch values), so ptxas cannot turn it into an ALU-pipe add/shift. The
+// ALU pipe is the saturated one in this kernel (ncu: 91 % busy, FMA pipe 5 %).
+__device__ __forceinline__ int imad(uint32_t a, int m, int c) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"((int)a), "r"(m), "r"(c));
+    return r;
 }
+struct Mul124 { int m1, m2, m4; };
 
-template <int W> __device__ __forceinline__ uint32_t hamming_words(const uint32_t (&a)[W], const uint32_t *b) {
-    uint32_t d = 0;
+// (Hamming distance of W words) + acc, with 4 POPC per 8 words: ones + 2*twos + 4*fours.
+template <int W>
+__device__ __forceinline__ int hamming_acc(const uint32_t (&a)[W], const uint32_t *b, int acc, const Mul124 &m) {
     if constexpr (W % 8 == 0) {
 #pragma unroll
         for (int g = 0; g < W / 8; g++) {
             uint32_t x[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) x[i] = a[g * 8 + i] ^ b[g * 8 + i];
-            d += popc8(x);
+            uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
+            csa(x[0], x[1], x[2], s1, c1);
+            csa(x[3], x[4], x[5], s2, c2);
+            csa(s1, s2, x[6], s3, c3);
+            csa(c1, c2, c3, s4, c4);
+            acc = imad(__popc(s3), m.m1, acc);
+            acc = imad(__popc(x[7]), m.m1, acc);
+            acc = imad(__popc(s4), m.m2, acc);
+            acc = imad(__popc(c4), m.m4, acc);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < W; i++) d += __popc(a[i] ^ b[i]);
+        for (int i = 0; i < W; i++) acc = imad(__popc(a[i] ^ b[i]), m.m1, acc);
     }
-    return d;
+    return acc;
 }
 
 constexpr int KNN_THREADS = 256;
@@ -64,9 +73,10 @@ template <int W, int QPT>
 __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint32_t *__restrict__ d1_base,
                                                               const uint32_t *__restrict__ d2_base,
                                                               size_t problem_stride_words, uint32_t n1, uint32_t n2,
-                                                              uint32_t split_len, uint32_t nsplits,
+                                                              uint32_t split_len, uint32_t nsplits, int one,
                                                               uint2 *__restrict__ part) {
     __shared__ __align__(16) uint32_t tile[2][KNN_TILE * W];
+    const Mul124 mul{one, one + one, one * 4};
     const uint32_t p = blockIdx.z, s = blockIdx.y, tid = threadIdx.x;
     const uint32_t *d1 = d1_base + (size_t)p * problem_stride_words;
     const uint32_t *d2 = d2_base + (size_t)p * problem_stride_words;
@@ -89,6 +99,9 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint32_t *__
     uint32_t bd1[QPT], bj1[QPT], bd2[QPT], bj2[QPT];
 #pragma unroll
     for (int k = 0; k < QPT; k++) { bd1[k] = bd2[k] = 0x3ffu; bj1[k] = bj2[k] = 0x3fffffu; }
+    int nbd2[QPT];   // -bd2: the distance is accumulated on top of it, so "d < bd2" is just a sign bit
+#pragma unroll
+    for (int k = 0; k < QPT; k++) nbd2[k] = -(int)bd2[k];
 
     constexpr int PIECES = KNN_TILE * W / 4;   // 16-byte pieces per tile
     auto issue_tile = [&](uint32_t tile_start, int buf) {
@@ -120,23 +133,25 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint32_t *__
                 const uint4 v = *reinterpret_cast<const uint4 *>(tb + j * W + 4 * i);
                 b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
             }
-            uint32_t d[QPT];
-            bool upd = false;
+            int t[QPT];
+            int sign = 0;
 #pragma unroll
             for (int k = 0; k < QPT; k++) {
-                d[k] = hamming_words<W>(a[k], b);
-                upd |= d[k] < bd2[k];
+                t[k] = hamming_acc<W>(a[k], b, nbd2[k], mul);   // d - bd2
+                sign |= t[k];
             }
             // The top-2 update is rare after the first few hundred candidates (probability ~2/j at
-            // candidate j); one warp vote keeps it off the common path instead of ~10 predicated
-            // instructions per distance.
-            if (__any_sync(0xffffffffu, upd)) {
+            // candidate j): one sign test and one warp vote per train descriptor keep it off the common
+            // path instead of ~10 predicated instructions per distance.
+            if (__any_sync(0xffffffffu, sign < 0)) {
                 const uint32_t jg = ts + j;
 #pragma unroll
                 for (int k = 0; k < QPT; k++)
-                    if (d[k] < bd2[k]) {   // equal distance never displaces an earlier (lower) index
-                        if (d[k] < bd1[k]) { bd2[k] = bd1[k]; bj2[k] = bj1[k]; bd1[k] = d[k]; bj1[k] = jg; }
-                        else { bd2[k] = d[k]; bj2[k] = jg; }
+                    if (t[k] < 0) {   // d < bd2; equal distance never displaces an earlier (lower) index
+                        const uint32_t d = (uint32_t)(t[k] + (int)bd2[k]);
+                        if (d < bd1[k]) { bd2[k] = bd1[k]; bj2[k] = bj1[k]; bd1[k] = d; bj1[k] = jg; }
+                        else { bd2[k] = d; bj2[k] = jg; }
+                        nbd2[k] = -(int)bd2[k];
                     }
             }
         }
@@ -240,13 +255,13 @@ template <int W> static void launch_partial(vb_ctx *ctx, const HammingPlan &pl, 
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
     if (pl.qpt == 4)
         k_knn2_partial<W, 4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d1, d2, stride_words, pl.n1, pl.n2, pl.split_len,
-                                                                    pl.nsplits, part);
+                                                                    pl.nsplits, 1, part);
     else if (pl.qpt == 2)
         k_knn2_partial<W, 2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d1, d2, stride_words, pl.n1, pl.n2, pl.split_len,
-                                                                    pl.nsplits, part);
+                                                                    pl.nsplits, 1, part);
     else
         k_knn2_partial<W, 1><<<grid, KNN_THREADS, 0, ctx->stream>>>(d1, d2, stride_words, pl.n1, pl.n2, pl.split_len,
-                                                                    pl.nsplits, part);
+                                                                    pl.nsplits, 1, part);
 }
 
 int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,

@@ -90,16 +90,55 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     if ((rc = ctx->ws_ensure(WS_DESC, desc_bytes))) return rc;
     if ((rc = ctx->ws_ensure(WS_RESULT, (size_t)P * sizeof(vb_pair_result)))) return rc;
     if (out_matches && (rc = ctx->ws_ensure(WS_OUTMATCH, (size_t)P * k * 8))) return rc;
-    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_PTS].p, pts, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_DESC].p, desc, desc_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = vb_pairs_run_d(ctx, ctx->ws[WS_PTS].as<float>(), ctx->ws[WS_DESC].as<uint8_t>(), nframes, k, bytes, params,
-                             ctx->ws[WS_RESULT].as<vb_pair_result>(),
-                             out_matches ? ctx->ws[WS_OUTMATCH].as<int32_t>() : nullptr)))
-        return rc;
-    VB_CUDA(cudaMemcpyAsync(results, ctx->ws[WS_RESULT].p, (size_t)P * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
-                            ctx->stream));
-    if (out_matches)
-        VB_CUDA(cudaMemcpyAsync(out_matches, ctx->ws[WS_OUTMATCH].p, (size_t)P * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // Software pipeline over sub-batches: the upload of batch b+1 and the download of batch b-1 run on two
+    // copy streams while batch b computes (they only overlap when the caller's buffers are pinned).
+    const uint32_t SB = (P >= 512) ? 256 : P;
+    const uint32_t nb = div_up(P, SB);
+    if (!ctx->copy_in) {
+        VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    while (ctx->events.size() < 2 * (size_t)nb + 1) {
+        cudaEvent_t e;
+        VB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    const uint32_t W = bytes / 4;
+    float *pts_d = ctx->ws[WS_PTS].as<float>();
+    uint8_t *desc_d = ctx->ws[WS_DESC].as<uint8_t>();
+    vb_pair_result *res_d = ctx->ws[WS_RESULT].as<vb_pair_result>();
+    int2 *outm_d = out_matches ? ctx->ws[WS_OUTMATCH].as<int2>() : nullptr;
+    // earlier work on the compute stream may still use these buffers
+    cudaEvent_t ev_prev = ctx->events[2 * nb];
+    VB_CUDA(cudaEventRecord(ev_prev, ctx->stream));
+    VB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_prev, 0));
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t f0 = b == 0 ? 0 : b * SB + 1;                       // first frame not yet uploaded
+        const uint32_t f1 = (b + 1 == nb) ? nframes : (b + 1) * SB + 1;    // one past the halo frame
+        VB_CUDA(cudaMemcpyAsync(pts_d + (size_t)f0 * k * 2, pts + (size_t)f0 * k * 2, (size_t)(f1 - f0) * k * 8,
+                                cudaMemcpyHostToDevice, ctx->copy_in));
+        VB_CUDA(cudaMemcpyAsync(desc_d + (size_t)f0 * k * bytes, desc + (size_t)f0 * k * bytes, (size_t)(f1 - f0) * k * bytes,
+                                cudaMemcpyHostToDevice, ctx->copy_in));
+        VB_CUDA(cudaEventRecord(ctx->events[b], ctx->copy_in));
+    }
+    const float2 *pts2 = reinterpret_cast<const float2 *>(pts_d);
+    const uint32_t *desc32 = reinterpret_cast<const uint32_t *>(desc_d);
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t p0 = b * SB, pb = (P - p0 < SB) ? P - p0 : SB;
+        VB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[b], 0));
+        rc = pairs_core(ctx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
+                        desc32 + (size_t)(p0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + p0,
+                        res_d + p0, outm_d ? outm_d + (size_t)p0 * k : nullptr);
+        if (rc) return rc;
+        VB_CUDA(cudaEventRecord(ctx->events[nb + b], ctx->stream));
+        VB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->events[nb + b], 0));
+        VB_CUDA(cudaMemcpyAsync(results + p0, res_d + p0, (size_t)pb * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
+                                ctx->copy_out));
+        if (out_matches)
+            VB_CUDA(cudaMemcpyAsync(out_matches + (size_t)p0 * k * 2, outm_d + (size_t)p0 * k, (size_t)pb * k * 8,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    VB_CUDA(cudaStreamSynchronize(ctx->copy_out));
     VB_CUDA(cudaStreamSynchronize(ctx->stream));
     return VB_OK;
 }
