@@ -51,6 +51,7 @@ struct RansacSelectArgs {
     const int2 *tent;       // [P][mcap] tentative matches (pair pipeline) or nullptr
     int2 *out_matches;      // [P][mcap] or nullptr
     int score_only;
+    int prefolded;          // cnt/score already hold the folded totals (k_fold ran first)
 };
 
 int ransac_plan(vb_ctx *ctx, uint32_t P, uint32_t mcap, uint32_t m_upper, uint32_t H, int min_items, RansacPlan *pl);
