@@ -266,18 +266,25 @@ template <int W> static void launch_partial(vb_ctx *ctx, const HammingPlan &pl, 
 
 int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                    KnnFinishArgs fin) {
-    ctx->prof_begin("hamming");
-    switch (pl.W) {
-        case 4: launch_partial<4>(ctx, pl, d1, d2, stride_words); break;
-        case 8: launch_partial<8>(ctx, pl, d1, d2, stride_words); break;
-        case 16: launch_partial<16>(ctx, pl, d1, d2, stride_words); break;
-        default: set_error("descriptor bytes must be 16, 32 or 64"); return VB_ERR_INVALID;
+    uint32_t nsplits = pl.nsplits;
+    if (hamming_tc_eligible(pl)) {
+        int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words);
+        if (rc) return rc;
+        nsplits = 1;
+    } else {
+        ctx->prof_begin("hamming");
+        switch (pl.W) {
+            case 4: launch_partial<4>(ctx, pl, d1, d2, stride_words); break;
+            case 8: launch_partial<8>(ctx, pl, d1, d2, stride_words); break;
+            case 16: launch_partial<16>(ctx, pl, d1, d2, stride_words); break;
+            default: set_error("descriptor bytes must be 16, 32 or 64"); return VB_ERR_INVALID;
+        }
+        ctx->prof_end("hamming");
+        ctx->launches++;
+        VB_CUDA(cudaGetLastError());
     }
-    ctx->prof_end("hamming");
-    ctx->launches++;
-    VB_CUDA(cudaGetLastError());
     fin.part = ctx->ws[WS_KNN_PART].as<uint2>();
-    fin.nsplits = pl.nsplits;
+    fin.nsplits = nsplits;
     fin.n1 = pl.n1;
     ctx->prof_begin("finish");
     k_knn2_finish<<<pl.P, 256, 0, ctx->stream>>>(fin);

@@ -32,6 +32,9 @@ struct KnnFinishArgs {
 };
 
 int hamming_plan(vb_ctx *ctx, uint32_t P, uint32_t n1, uint32_t n2, uint32_t bytes, HammingPlan *pl);
+// tensor-core path (hamming_tc.cu): 256-bit descriptors, fills WS_KNN_PART with one split
+bool hamming_tc_eligible(const HammingPlan &pl);
+int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words);
 int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                    KnnFinishArgs fin);
 
