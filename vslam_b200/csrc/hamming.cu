@@ -267,8 +267,9 @@ template <int W> static void launch_partial(vb_ctx *ctx, const HammingPlan &pl, 
 int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                    KnnFinishArgs fin) {
     uint32_t nsplits = pl.nsplits;
+    const uint2 *part = nullptr;
     if (hamming_tc_eligible(pl)) {
-        int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words);
+        int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words, &part);
         if (rc) return rc;
         nsplits = 1;
     } else {
@@ -282,8 +283,9 @@ int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const
         ctx->prof_end("hamming");
         ctx->launches++;
         VB_CUDA(cudaGetLastError());
+        part = ctx->ws[WS_KNN_PART].as<uint2>();
     }
-    fin.part = ctx->ws[WS_KNN_PART].as<uint2>();
+    fin.part = part;
     fin.nsplits = nsplits;
     fin.n1 = pl.n1;
     ctx->prof_begin("finish");

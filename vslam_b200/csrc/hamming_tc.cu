@@ -28,7 +28,8 @@ namespace vb {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_COLSPLIT = 2;         // threads draining one accumulator row (column parts)
+constexpr int TC_THREADS = 128 + 256 * TC_COLSPLIT;   // 4 service warps + draining warps
 constexpr int TC_QROWS = 256;          // queries per CTA
 constexpr int TC_NCOLS = 256;          // train descriptors per tile (UMMA N)
 constexpr int TC_KBYTES = 256;         // expanded descriptor: 256 e4m3 values
@@ -54,43 +55,56 @@ __global__ void __launch_bounds__(256) k_expand_pm1(const uint32_t *__restrict__
     for (int i = 0; i < 4; i++) {
         const uint32_t nib = (bits >> (4 * i)) & 0xfu;
         const uint32_t spread = (nib * 0x00204081u) & 0x01010101u;   // bit i -> LSB of byte i
-        o[i] = 0x38383838u | (spread << 7);                          // e4m3: 0x38 = +1.0, 0xB8 = -1.0
+        o[i] = 0x70707070u | (spread << 7);                          // e4m3: 0x70 = +128, 0xF0 = -128
     }
     *reinterpret_cast<uint4 *>(dst + grow * TC_KBYTES + piece * 16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-struct Top2 {
-    float d1, d2;      // largest and second largest dot (= smallest and second smallest distance)
-    uint32_t i1, i2;
-    __device__ __forceinline__ void offer(float v, uint32_t col) {
-        if (v > d2) {   // strictly better than the current second; an equal dot never displaces an earlier index
-            if (v > d1) { d2 = d1; i2 = i1; d1 = v; i1 = col; }
-            else { d2 = v; i2 = col; }
-        }
-    }
-};
+// ---- the drain ---------------------------------------------------------------------------------------
+// An accumulator value is v = 2^14 * dot (see k_expand_pm1). A candidate's key is  col - v  =
+// 2^14 * (2 * distance - 256) + col: an integer of magnitude below 2^23, exact in fp32, whose order is
+// (distance, train index) — knnMatch's order including its lower-index-first ties. Keys are never equal.
+//
+// Per 32-column chunk a thread forms the 32 keys (one FADD each, immediate column operand, FMA pipe), takes
+// their minimum with a 3-input min tree (16 FMNMX3/FMNMX, ALU pipe) and offers that single key to its running
+// (r0 <= r1). There is no branch, no vote and no data-dependent work. What this yields per row is the best
+// candidate and the best candidate OUTSIDE the best's own chunk; the only thing it can miss is a second
+// nearest neighbour that shares the best's 32-column chunk, which k_knn2_tc_fix settles afterwards by
+// evaluating those 31 distances directly (XOR + POPC on the original descriptors).
+constexpr int TC_KEY_SHIFT = 14;
+constexpr uint32_t TC_MAX_TRAIN = 1u << TC_KEY_SHIFT;
+constexpr float TC_KEY_BIAS = 4194304.f;   // 2^22 = 2^14 * 256: makes keys non-negative
+constexpr float TC_KEY_NONE = 3.0e7f;      // above every real key (< 2^24)
 
-template <bool MASKED>
-__device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[32], uint32_t col0, uint32_t n2, Top2 &t) {
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// min over the chunk's keys, columns counted from the start of the warp's column part (c0 = 32 * chunk)
+template <int C0, bool MASKED>
+__device__ __forceinline__ float chunk_min_key(const uint32_t (&raw)[32], uint32_t nvalid) {
+    float k[32];
 #pragma unroll
-    for (int g = 0; g < 32; g += 4) {
-        float v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = __uint_as_float(raw[g + i]);
-            if (MASKED) v[i] = (col0 + g + i < n2) ? v[i] : -1.0e30f;
-        }
-        const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-        if (__any_sync(0xffffffffu, m > t.d2)) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) t.offer(v[i], col0 + g + i);
-        }
+    for (int i = 0; i < 32; i++) {
+        k[i] = __fsub_rn((float)(C0 + i), __uint_as_float(raw[i]));
+        if (MASKED) k[i] = (uint32_t)(C0 + i) < nvalid ? k[i] : TC_KEY_NONE;
     }
+    float a[12];
+#pragma unroll
+    for (int i = 0; i < 10; i++) a[i] = min3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+    a[10] = k[30];
+    a[11] = k[31];
+    const float b0 = min3(a[0], a[1], a[2]), b1 = min3(a[3], a[4], a[5]), b2 = min3(a[6], a[7], a[8]),
+                b3 = min3(a[9], a[10], a[11]);
+    return fminf(min3(b0, b1, b2), b3);
+}
+
+__device__ __forceinline__ void offer(float k, float &r0, float &r1) {
+    r1 = fminf(r1, fmaxf(r0, k));
+    r0 = fminf(r0, k);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
-          uint32_t rowstride_q, uint32_t rowstride_t, uint2 *__restrict__ part) {
+          uint32_t rowstride_q, uint32_t rowstride_t, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
     const uint32_t sA = smem0;
@@ -114,7 +128,7 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);   // one arrival per draining warp
+            mbar_init(bar_tempty + 8 * s, 4 * TC_COLSPLIT);   // one arrival per draining warp
         }
         fence_barrier_init();
     }
@@ -138,6 +152,10 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             for (uint32_t j = 0; j < ntiles; j++) {
                 const uint32_t s = j & 1, ph = (j >> 1) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                if ((dbg & 4) && j >= 2) {   // measurement only: reuse the resident stage, no L2 -> SM traffic
+                    mbar_arrive(bar_full + 8 * s);
+                    continue;
+                }
                 mbar_expect_tx(bar_full + 8 * s, TC_B_BYTES);
                 const uint32_t dst = sB + s * TC_B_BYTES;
 #pragma unroll
@@ -175,36 +193,63 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             }
         }
     } else if (warp >= 4) {
-        const uint32_t h = (warp - 4) >> 2, quad = warp & 3;
+        const uint32_t ew = warp - 4;
+        const uint32_t quad = warp & 3, h = (ew >> 2) & 1, ch = ew >> 3;   // TMEM lane quadrant, accumulator, column part
         const uint32_t row = h * 128 + quad * 32 + lane;
         const uint32_t q = q0 + row;
-        const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + h * TC_NCOLS;
-        Top2 t;
-        t.d1 = t.d2 = -1.0e30f;
-        t.i1 = t.i2 = KNN_IDX_MASK;
-        for (uint32_t j = 0; j < ntiles; j++) {
+        constexpr uint32_t CW = TC_NCOLS / TC_COLSPLIT;
+        constexpr int NCH = CW / 32;
+        static_assert(NCH == 4, "the drain below is written out for four 32-column chunks per warp");
+        const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + h * TC_NCOLS + ch * CW;
+        // running (best, best outside the best's chunk) as biased global keys
+        float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
+        float tbase = (float)(ch * CW) + TC_KEY_BIAS;   // key bias + first column of this warp's part of tile j
+        uint32_t raw0[32], raw1[32];
+        for (uint32_t j = 0; j < ntiles; j++, tbase += (float)TC_NCOLS) {
             mbar_wait(bar_tfull + 8 * h, j & 1);
             tc_fence_after();
-            const uint32_t tile0 = j * TC_NCOLS;
-            const bool masked = tile0 + TC_NCOLS > n2;
-#pragma unroll 1
-            for (int c = 0; c < TC_NCOLS / 32; c++) {
-                uint32_t raw[32];
-                tmem_ld32(taddr + c * 32, raw);
-                tmem_wait_ld();
-                if (c == TC_NCOLS / 32 - 1) {   // the accumulator is in registers: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-                }
-                if (masked) drain_chunk<true>(raw, tile0 + c * 32, n2, t);
-                else drain_chunk<false>(raw, tile0 + c * 32, n2, t);
+            const uint32_t tile0 = j * TC_NCOLS + ch * CW;
+            if ((dbg & 2) || tile0 >= n2) {   // (dbg 2: MMA floor measurement) / nothing valid in this part of the last tile
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                continue;
             }
+            const bool masked = tile0 + CW > n2;
+            const uint32_t nvalid = n2 - tile0;
+            float m[NCH];
+            // chunk c+1 is in flight while chunk c is reduced; the accumulator goes back to the MMA warp as soon
+            // as its last chunk has landed in registers
+            tmem_ld32(taddr, raw0);
+            tmem_wait_ld_regs(raw0);
+            tmem_ld32(taddr + 32, raw1);
+            m[0] = masked ? chunk_min_key<0, true>(raw0, nvalid) : chunk_min_key<0, false>(raw0, nvalid);
+            tmem_wait_ld_regs(raw1);
+            tmem_ld32(taddr + 64, raw0);
+            m[1] = masked ? chunk_min_key<32, true>(raw1, nvalid) : chunk_min_key<32, false>(raw1, nvalid);
+            tmem_wait_ld_regs(raw0);
+            tmem_ld32(taddr + 96, raw1);
+            m[2] = masked ? chunk_min_key<64, true>(raw0, nvalid) : chunk_min_key<64, false>(raw0, nvalid);
+            tmem_wait_ld_regs(raw1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+            m[3] = masked ? chunk_min_key<96, true>(raw1, nvalid) : chunk_min_key<96, false>(raw1, nvalid);
+#pragma unroll
+            for (int c = 0; c < NCH; c++) offer(__fadd_rn(m[c], tbase), r0, r1);
         }
         if (q < n1) {
-            const uint32_t h1 = (uint32_t)((256 - __float2int_rn(t.d1)) >> 1);
-            const uint32_t h2 = (uint32_t)((256 - __float2int_rn(t.d2)) >> 1);
-            part[(size_t)p * n1 + q] = make_uint2((h1 << KNN_IDX_BITS) | t.i1, (h2 << KNN_IDX_BITS) | t.i2);
+            // biased key -> (distance << KNN_IDX_BITS | index); a part that saw fewer than two chunks reports the
+            // largest key, which the merge ignores
+            uint32_t out[2];
+            const float ks[2] = {r0, r1};
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const uint32_t ki = __float2uint_rz(ks[i]);
+                out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                            : 0xffffffffu;
+            }
+            part[((size_t)p * TC_COLSPLIT + ch) * n1 + q] = make_uint2(out[0], out[1]);
         }
     }
     tc_fence_before();
@@ -215,32 +260,86 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
 }
 
+// One warp per query: merge the column parts, then settle the one case the drain leaves open — a second
+// nearest neighbour inside the best's own 32-column chunk — by evaluating that chunk's other 31 distances
+// with XOR + POPC on the original descriptors. out[p][q] = final (best, second) keys.
+__global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
+                                                     size_t stride_words, uint32_t n1, uint32_t n2,
+                                                     const uint2 *__restrict__ part, uint2 *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), p = blockIdx.y;
+    if (q >= n1) return;
+    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+#pragma unroll
+    for (int s = 0; s < TC_COLSPLIT; s++) {
+        const uint2 v = part[((size_t)p * TC_COLSPLIT + s) * n1 + q];
+        const uint32_t lo = min(k1, v.x), hi = max(k1, v.x);   // v.x < v.y and k1 < k2
+        k2 = min(min(k2, v.y), hi);
+        k1 = lo;
+    }
+    const uint32_t i1 = k1 & KNN_IDX_MASK;
+    const uint32_t col = (i1 & ~31u) + lane;
+    uint32_t key = 0xffffffffu;
+    if (col < n2 && col != i1) {
+        const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
+        const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
+        const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+        const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        key = (d << KNN_IDX_BITS) | col;
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) out[(size_t)p * n1 + q] = make_uint2(k1, min(k2, key));
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol. It is resolved through the runtime at first use instead of being
+// linked, so libvslam_b200.so loads (and its exports can be listed) on a machine without libcuda.so.1.
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_fn tensor_map_encode() {
+    static tensor_map_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tensor_map_encode_fn>(p);
+    }
+    return fn;
+}
+
 static int make_map(CUtensorMap *m, const void *base, uint64_t rows) {
     const cuuint64_t gdim[2] = {(cuuint64_t)TC_KBYTES, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)TC_KBYTES};
     const cuuint32_t box[2] = {128, (cuuint32_t)TC_BOX_ROWS};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride,
-                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    tensor_map_encode_fn enc = tensor_map_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return VB_ERR_CUDA;
+    }
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        const char *s = nullptr;
-        cuGetErrorString(r, &s);
-        set_error("cuTensorMapEncodeTiled -> %s", s ? s : "?");
+        set_error("cuTensorMapEncodeTiled -> CUresult %d", (int)r);
         return VB_ERR_CUDA;
     }
     return VB_OK;
 }
 
 bool hamming_tc_eligible(const HammingPlan &pl) {
-    if (pl.W != 8 || pl.n2 > KNN_IDX_MASK) return false;
+    if (pl.W != 8 || pl.n2 > TC_MAX_TRAIN) return false;   // the packed float key holds 14 index bits
     if (const char *e = getenv("VB_HAMMING_TC")) return atoi(e) != 0;
     // below a few thousand distance tiles the popcount kernel's finer CTA granularity wins
     return (uint64_t)pl.P * pl.n1 * pl.n2 >= (1ull << 22);
 }
 
-// Fills WS_KNN_PART as [P][1 split][n1], the layout k_knn2_finish reads with nsplits = 1.
-int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words) {
+// WS_KNN_PART = [P][TC_COLSPLIT][n1] column-part results followed by [P][n1] final keys; *final_part points at
+// the latter, which k_knn2_finish reads as a single split.
+int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
+                      const uint2 **final_part) {
     static bool attr_set = false;
     if (!attr_set) {
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -251,7 +350,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * TC_KBYTES))) return rc;
-    if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * n1 * sizeof(uint2)))) return rc;
+    if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (TC_COLSPLIT + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
     ctx->prof_begin("expand");
@@ -273,10 +372,17 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     if ((rc = make_map(&mt, Et, (uint64_t)P * n2))) return rc;
     dim3 grid(div_up(n1, TC_QROWS), P);
     ctx->prof_begin("hamming");
-    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, ctx->ws[WS_KNN_PART].as<uint2>());
+    uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
+    uint2 *fixed = part + (size_t)P * TC_COLSPLIT * n1;
+    static const int dbg = getenv("VB_TC_DBG") ? atoi(getenv("VB_TC_DBG")) : 0;
+    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, part, dbg);
     ctx->prof_end("hamming");
-    ctx->launches++;
+    ctx->prof_begin("knnfix");
+    k_knn2_tc_fix<<<dim3(div_up(n1, 8), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
+    ctx->prof_end("knnfix");
+    ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
+    *final_part = fixed;
     return VB_OK;
 }
 

@@ -105,6 +105,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// TMEM -> registers, 4 consecutive columns of this warp's 32 rows.
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld_regs4(uint32_t (&v)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]) : : "memory");
+}
+
+// tcgen05.wait::ld that also names the destination registers of the load it completes as in/out operands, so
+// the compiler cannot schedule a use of them above the wait (the load is asynchronous).
+__device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand stored as [rows][128 B] with the 128-byte swizzle
 // (what a TMA box of 128 B x rows with CU_TENSOR_MAP_SWIZZLE_128B produces; tile base 1024-aligned):
