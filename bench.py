@@ -37,12 +37,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 METRIC = "frame pairs/sec (match+RANSAC) at 5k kpts"
 UNIT = "pairs/s"
+DTYPE = "u8 descriptors as e4m3 +-128 on tcgen05 (exact integer Hamming) + f32/f64 residual"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1025, help="frames per rank (pairs = frames-1)")
@@ -67,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -99,10 +100,24 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source). Driver-written MEASURED_PEAKS.json, else the profiling guide's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1614.4)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1614.4, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, pairs, kpts, hyps):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of
+    this same workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), or None when the shapes differ."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        if (d["pairs"], d["kpts"], d["hyps"]) == (pairs, kpts, hyps):
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -137,7 +152,7 @@ def run_reference(args, rank, world):
     from vslam_b200 import synth
     orc = cpu_oracle()
     cores = os.cpu_count() or 1
-    sample = int(min(args.frames - 1, max(2 * cores, 8)))
+    sample = int(min(args.frames - 1, max(8 * cores, 64)))   # ~1-2 s of host work per step
     pts, desc = synth.sequence(sample + 1, args.kpts, 1000)
     for _ in range(args.warmup):
         cpu_pairs_per_s(orc, pts, desc, min(sample, cores), args.hyps, args.threshold, 1, threads=cores)
@@ -149,7 +164,7 @@ def run_reference(args, rank, world):
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8 popcount + f32/f64 residual", "data": "synthetic",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": workload_config(args, sample),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                              "sample": f"{sample} pairs per step x {args.steps} steps, OpenMP over pairs"},
@@ -244,7 +259,6 @@ def main():
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop()
     value = world * P * args.steps / (ms_total * 1e-3)
 
     # sanity: the timed path produced real results
@@ -257,7 +271,7 @@ def main():
     ctx.profile(True)
     step_device()
     torch.cuda.synchronize(dev)
-    kt = {name: ctx.profile_ms(name) for name in ("hamming", "finish", "sample", "solve", "score", "select")}
+    kt = {name: ctx.profile_ms(name) for name in ("expand", "hamming", "knnfix", "finish", "sample", "solve", "score", "select")}
     ctx.profile(False)
     # k_score: profile it over several launches of the timed workload for the roofline figure
     score_ms = []
@@ -268,12 +282,13 @@ def main():
         score_ms.append(ctx.profile_ms("score"))
         ctx.profile(False)
     score_ms_avg = float(np.mean(score_ms))
-    peak, peak_src = measured_peaks()
+    peak, bf16_peak, peak_src = measured_peaks()
     evals = float(args.hyps) * float(sum_tent)                    # (hypothesis, match) evaluations per launch
     logical_bytes = 16.0 * evals + 36.0 * args.hyps * P + 8.0 * args.hyps * P
     achieved = logical_bytes / (score_ms_avg * 1e-3) / 1e9
     roofline = {"kernel": "k_score (RANSAC residual / inlier scoring)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic("k_score", P, k, args.hyps),
                 "peak_source": peak_src, "evals_per_launch": evals, "ms_per_launch": score_ms_avg,
                 "hypotheses_scored_per_s": args.hyps * P / (score_ms_avg * 1e-3),
                 "note": "logical bytes = 16 B x hypotheses x matches (SURVEY 8d); tiles are L2/smem resident so DRAM "
@@ -291,6 +306,7 @@ def main():
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()   # sampled every 20 ms across both timed regions (device-resident and end-to-end)
     res_e = res_h.numpy().view(PAIR_RESULT_DTYPE)
     assert np.array_equal(res_e["n_matches"], res["n_matches"]), "e2e and device-resident paths disagree"
     e2e = {"value": world * P * e_steps / e2e_s, "unit": UNIT,
@@ -312,7 +328,8 @@ def main():
         orc = cpu_oracle()
         cores = os.cpu_count() or 1
         v1, _, dt1, _ = cpu_pairs_per_s(orc, pts, desc, 2, args.hyps, args.threshold, 1, threads=1)
-        sample = int(min(P, max(cores, 8)))
+        vq, _, _, _ = cpu_pairs_per_s(orc, pts, desc, int(min(P, max(cores, 8))), args.hyps, args.threshold, 1, threads=cores)
+        sample = int(min(P, max(cores, 8, vq * 12.0)))   # about 10 s of host work, never more than the step itself
         vN, used, dtN, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=cores)
         # parity spot check of the timed GPU output against the same oracle (first pair)
         o = orc.match_features(pts[0], desc[0], pts[1], desc[1], 0.7, 8, args.hyps, args.threshold, 1)
@@ -324,12 +341,11 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8 popcount + f32/f64 residual", "data": "synthetic",
+                "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
                 "config": workload_config(args, P), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "kernel_ms": kt, "kernel_share_of_step": shares,
-                "hamming": {"pair_distances_per_s": float(P) * k * k / (kt["hamming"] * 1e-3) if kt["hamming"] > 0 else None,
-                            "popc_per_pair_distance": 4, "note": "integer-pipe bound (XOR+LOP3 CSA+POPC), not HBM"},
+                "hamming": hamming_roofline(P, k, kt["hamming"], bf16_peak, peak_src),
                 "single_pair_match_features_ms": single_ms,
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
@@ -341,6 +357,17 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def hamming_roofline(P, k, ms, bf16_peak, peak_src):
+    """Second kernel of the step: k_knn2_tc, tensor-pipe bound. Algorithmic work = 2 * 256 flop per descriptor pair
+    (256-term +-1 dot product). fp8 peak = 2 x the measured dense bf16 figure (same tensor pipe, K = 32 vs 16 per MMA)."""
+    if not ms or ms <= 0:
+        return None
+    tf = 2.0 * 256.0 * float(P) * k * k / (ms * 1e-3) / 1e12
+    return {"kernel": "k_knn2_tc (tcgen05 kind::f8f6f4, e4m3 +-128)", "bound": "tensor", "achieved": tf, "peak": 2.0 * bf16_peak,
+            "unit": "TFLOP/s", "frac": tf / (2.0 * bf16_peak), "peak_source": peak_src + ", fp8 = 2 x bf16",
+            "ms_per_launch": ms, "pair_distances_per_s": float(P) * k * k / (ms * 1e-3)}
 
 
 def kdtree_stage(ctx, torch, dev, pts, k):

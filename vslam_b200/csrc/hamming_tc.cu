@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "hamming_dev.cuh"
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 
 namespace vb {
 
@@ -292,41 +293,8 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
     if (lane == 0) out[(size_t)p * n1 + q] = make_uint2(k1, min(k2, key));
 }
 
-// cuTensorMapEncodeTiled is a driver-API symbol. It is resolved through the runtime at first use instead of being
-// linked, so libvslam_b200.so loads (and its exports can be listed) on a machine without libcuda.so.1.
-typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static tensor_map_encode_fn tensor_map_encode() {
-    static tensor_map_encode_fn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tensor_map_encode_fn>(p);
-    }
-    return fn;
-}
-
 static int make_map(CUtensorMap *m, const void *base, uint64_t rows) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)TC_KBYTES, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)TC_KBYTES};
-    const cuuint32_t box[2] = {128, (cuuint32_t)TC_BOX_ROWS};
-    const cuuint32_t estr[2] = {1, 1};
-    tensor_map_encode_fn enc = tensor_map_encode();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return VB_ERR_CUDA;
-    }
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled -> CUresult %d", (int)r);
-        return VB_ERR_CUDA;
-    }
-    return VB_OK;
+    return tc::make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, TC_KBYTES, rows, 128, TC_BOX_ROWS);
 }
 
 bool hamming_tc_eligible(const HammingPlan &pl) {
