@@ -406,3 +406,48 @@ def test_knn2_l2f_bit_exact(ctx, oracle, n1, n2, dim):
     oidx, odist = oracle.knn2_l2f(d1, d2)
     assert np.array_equal(idx, oidx) and np.array_equal(bits(dist), bits(odist))
     assert np.array_equal(ctx.match_l2f(d1, d2, 0.7), oracle.match_l2f(d1, d2, 0.7))
+
+
+def _float_descriptors(kind, n1, n2, dim, seed):
+    rng = np.random.default_rng(seed)
+    d1 = rng.standard_normal((n1, dim)).astype(np.float32)
+    d2 = rng.standard_normal((n2, dim)).astype(np.float32)
+    if kind == "unit":            # unit-norm, half of the queries are noisy copies of train rows
+        d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+        d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+        m = min(n1, n2) // 2
+        d1[:m] = d2[:m] + 0.05 * rng.standard_normal((m, dim)).astype(np.float32)
+    elif kind == "sift":          # integer-valued, large norms: many exactly equal distances
+        d1, d2 = np.abs(d1 * 40).round().astype(np.float32), np.abs(d2 * 40).round().astype(np.float32)
+    elif kind == "equal":         # every train row equal but one: every chunk minimum ties, exact scan fallback
+        d2[:] = d2[0]
+        d2[min(7, n2 - 1)] += 1e-3
+    if n2 > 40:                   # duplicated train rows (tie order) and a zero distance
+        d2[n2 // 2] = d2[3]
+        d1[min(5, n1 - 1)] = d2[3]
+    return np.ascontiguousarray(d1), np.ascontiguousarray(d2)
+
+
+@pytest.mark.parametrize("kind,n1,n2,dim", [("unit", 256, 256, 128), ("unit", 300, 700, 64), ("gauss", 1000, 513, 128),
+                                            ("sift", 1500, 2100, 128), ("unit", 37, 2, 128), ("equal", 500, 40, 64),
+                                            ("equal", 300, 1000, 128), ("sift", 700, 300, 64)])
+def test_knn2_l2f_tensor_path_bit_exact(ctx, oracle, monkeypatch, kind, n1, n2, dim):
+    """The tcgen05 (bf16 GEMM + exact re-evaluation) path returns the oracle's indices and distance bits."""
+    monkeypatch.setenv("VB_L2_TC", "1")
+    d1, d2 = _float_descriptors(kind, n1, n2, dim, 11)
+    idx, dist = ctx.knn2_l2f(d1, d2)
+    oidx, odist = oracle.knn2_l2f(d1, d2)
+    assert np.array_equal(idx, oidx) and np.array_equal(bits(dist), bits(odist))
+    assert np.array_equal(ctx.match_l2f(d1, d2, 0.7), oracle.match_l2f(d1, d2, 0.7))
+
+
+def test_knn2_l2f_tensor_path_equals_exact_kernel_at_size(ctx, oracle, monkeypatch):
+    """6000 x 7000 x 128: tensor path == exact SIMT kernel on every query, == oracle on a slice."""
+    d1, d2 = _float_descriptors("unit", 6000, 7000, 128, 3)
+    monkeypatch.setenv("VB_L2_TC", "1")
+    it, dt = ctx.knn2_l2f(d1, d2)
+    monkeypatch.setenv("VB_L2_TC", "0")
+    ie, de = ctx.knn2_l2f(d1, d2)
+    assert np.array_equal(it, ie) and np.array_equal(bits(dt), bits(de))
+    oi, od = oracle.knn2_l2f(np.ascontiguousarray(d1[:200]), d2)
+    assert np.array_equal(it[:200], oi) and np.array_equal(bits(dt[:200]), bits(od))

@@ -13,6 +13,10 @@
 
 namespace vb {
 
+// tensor-core path (l2f_tc.cu): same results, large problems
+bool l2_tc_eligible(uint32_t n1, uint32_t n2, uint32_t dim);
+int l2_tc_launch(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, uint32_t n2, uint32_t dim, ulonglong2 *out);
+
 constexpr int L2_THREADS = 128;
 constexpr int L2_TILE = 32;
 
@@ -135,8 +139,9 @@ static int l2_host(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, u
     if (n1 == 0) { if (out_m) *out_m = 0; return VB_OK; }
     VB_CUDA(cudaSetDevice(ctx->device));
     int rc;
+    const bool use_tc = l2_tc_eligible(n1, n2, dim);
     const uint32_t qtiles = div_up(n1, L2_THREADS);
-    uint32_t ns = div_up(4u * ctx->sm_count, qtiles);
+    uint32_t ns = use_tc ? 1 : div_up(4u * ctx->sm_count, qtiles);
     const uint32_t max_splits = div_up(n2, L2_TILE);
     if (ns > max_splits) ns = max_splits;
     if (ns > 64) ns = 64;
@@ -152,6 +157,11 @@ static int l2_host(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, u
     VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_L2A].p, d1, (size_t)n1 * dim * 4, cudaMemcpyHostToDevice, ctx->stream));
     VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_L2B].p, d2, (size_t)n2 * dim * 4, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid(qtiles, nsplits);
+    if (use_tc) {
+        if ((rc = l2_tc_launch(ctx, ctx->ws[WS_L2A].as<float>(), n1, ctx->ws[WS_L2B].as<float>(), n2, dim,
+                               ctx->ws[WS_L2C].as<ulonglong2>())))
+            return rc;
+    } else {
     ctx->prof_begin("l2f");
     if (dim == 128)
         k_l2_partial<128><<<grid, L2_THREADS, 0, ctx->stream>>>(ctx->ws[WS_L2A].as<float>(), ctx->ws[WS_L2B].as<float>(), n1,
@@ -160,11 +170,13 @@ static int l2_host(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, u
         k_l2_partial<64><<<grid, L2_THREADS, 0, ctx->stream>>>(ctx->ws[WS_L2A].as<float>(), ctx->ws[WS_L2B].as<float>(), n1,
                                                               n2, split_len, nsplits, ctx->ws[WS_L2C].as<ulonglong2>());
     ctx->prof_end("l2f");
+    ctx->launches++;
+    }
     int32_t *kidx = ctx->ws[WS_KNN].as<int32_t>();
     float *kdist = reinterpret_cast<float *>(kidx + (size_t)n1 * 2);
     k_l2_finish<<<1, 256, 0, ctx->stream>>>(ctx->ws[WS_L2C].as<ulonglong2>(), nsplits, n1, ratio, kidx, kdist,
                                             ctx->ws[WS_TENT].as<int2>(), ctx->ws[WS_M].as<uint32_t>());
-    ctx->launches += 2;
+    ctx->launches++;
     VB_CUDA(cudaGetLastError());
     uint32_t m = 0;
     VB_CUDA(cudaMemcpyAsync(&m, ctx->ws[WS_M].p, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -81,6 +81,15 @@ __device__ __forceinline__ void umma_f8f6f4(uint32_t d_tmem, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 (fp16 / bf16 operands, K = 16 per instruction).
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // kind::tf32 (fp32 containers read as tf32, K = 8 per instruction).
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -148,6 +157,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // Instruction descriptor (upper word of the UMMA "idesc"): D format [4,6) (1 = f32), A format [7,10),
 // B format [10,13), A/B major [15],[16] (0 = K-major), N >> 3 at [17,23), M >> 4 at [24,29).
 constexpr uint32_t UMMA_FMT_E4M3 = 0;   // kind::f8f6f4
+constexpr uint32_t UMMA_FMT_BF16 = 1;   // kind::f16 (0 = fp16)
 constexpr uint32_t UMMA_FMT_TF32 = 2;   // kind::tf32
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt_ab, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt_ab << 7) | (fmt_ab << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
