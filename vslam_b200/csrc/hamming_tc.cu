@@ -66,12 +66,14 @@ __global__ void __launch_bounds__(256) k_expand_pm1(const uint32_t *__restrict__
 // 2^14 * (2 * distance - 256) + col: an integer of magnitude below 2^23, exact in fp32, whose order is
 // (distance, train index) — knnMatch's order including its lower-index-first ties. Keys are never equal.
 //
-// Per 32-column chunk a thread forms the 32 keys (one FADD each, immediate column operand, FMA pipe), takes
-// their minimum with a 3-input min tree (16 FMNMX3/FMNMX, ALU pipe) and offers that single key to its running
-// (r0 <= r1). There is no branch, no vote and no data-dependent work. What this yields per row is the best
-// candidate and the best candidate OUTSIDE the best's own chunk; the only thing it can miss is a second
-// nearest neighbour that shares the best's 32-column chunk, which k_knn2_tc_fix settles afterwards by
-// evaluating those 31 distances directly (XOR + POPC on the original descriptors).
+// Per 32-column chunk a thread forms the 32 keys (one FADD each, immediate column operand, FMA pipe), reduces
+// every 8-column group to its minimum key with a 3-input min tree (4 FMNMX3/FMNMX, ALU pipe) and offers the four
+// group minima, two at a time, to its running (r0 <= r1). There is no branch, no vote and no data-dependent
+// work. What this yields per row is the best candidate and the best candidate OUTSIDE the best's own group; the
+// only thing it can miss is a second nearest neighbour that shares the best's 8-column group, which
+// k_knn2_tc_fix settles afterwards by evaluating those 7 distances directly (XOR + POPC on the original
+// descriptors). (One key per 32-column chunk costs 7 ALU instructions per chunk less here, but makes the fix
+// read 1 KB of descriptors per query: 0.78 ms per 1024 pairs against 0.2 ms.)
 constexpr int TC_KEY_SHIFT = 14;
 constexpr uint32_t TC_MAX_TRAIN = 1u << TC_KEY_SHIFT;
 constexpr float TC_KEY_BIAS = 4194304.f;   // 2^22 = 2^14 * 256: makes keys non-negative
@@ -79,28 +81,29 @@ constexpr float TC_KEY_NONE = 3.0e7f;      // above every real key (< 2^24)
 
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-// min over the chunk's keys, columns counted from the start of the warp's column part (c0 = 32 * chunk)
-template <int C0, bool MASKED>
-__device__ __forceinline__ float chunk_min_key(const uint32_t (&raw)[32], uint32_t nvalid) {
-    float k[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        k[i] = __fsub_rn((float)(C0 + i), __uint_as_float(raw[i]));
-        if (MASKED) k[i] = (uint32_t)(C0 + i) < nvalid ? k[i] : TC_KEY_NONE;
-    }
-    float a[12];
-#pragma unroll
-    for (int i = 0; i < 10; i++) a[i] = min3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
-    a[10] = k[30];
-    a[11] = k[31];
-    const float b0 = min3(a[0], a[1], a[2]), b1 = min3(a[3], a[4], a[5]), b2 = min3(a[6], a[7], a[8]),
-                b3 = min3(a[9], a[10], a[11]);
-    return fminf(min3(b0, b1, b2), b3);
+// One 32-column chunk of one row: the four minimum keys of its 8-column groups go into the running (r0 <= r1).
+// Columns are counted from the start of the warp's column part (C0 = 32 * chunk); `base` makes them global.
+constexpr int TC_GROUP = 8;   // columns represented by one offered key (what k_knn2_tc_fix re-examines)
+__device__ __forceinline__ void offer2(float a, float b, float &r0, float &r1) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    r1 = min3(r1, fmaxf(r0, lo), hi);
+    r0 = fminf(r0, lo);
 }
-
-__device__ __forceinline__ void offer(float k, float &r0, float &r1) {
-    r1 = fminf(r1, fmaxf(r0, k));
-    r0 = fminf(r0, k);
+template <int C0, bool MASKED>
+__device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[32], uint32_t nvalid, float base, float &r0, float &r1) {
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float k[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            k[i] = __fsub_rn((float)(C0 + 8 * j + i), __uint_as_float(raw[8 * j + i]));
+            if (MASKED) k[i] = (uint32_t)(C0 + 8 * j + i) < nvalid ? k[i] : TC_KEY_NONE;
+        }
+        g[j] = __fadd_rn(fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), k[6]), k[7]), base);
+    }
+    offer2(g[0], g[1], r0, r1);
+    offer2(g[2], g[3], r0, r1);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -218,26 +221,23 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             }
             const bool masked = tile0 + CW > n2;
             const uint32_t nvalid = n2 - tile0;
-            float m[NCH];
             // chunk c+1 is in flight while chunk c is reduced; the accumulator goes back to the MMA warp as soon
             // as its last chunk has landed in registers
             tmem_ld32(taddr, raw0);
             tmem_wait_ld_regs(raw0);
             tmem_ld32(taddr + 32, raw1);
-            m[0] = masked ? chunk_min_key<0, true>(raw0, nvalid) : chunk_min_key<0, false>(raw0, nvalid);
+            if (masked) drain_chunk<0, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<0, false>(raw0, nvalid, tbase, r0, r1);
             tmem_wait_ld_regs(raw1);
             tmem_ld32(taddr + 64, raw0);
-            m[1] = masked ? chunk_min_key<32, true>(raw1, nvalid) : chunk_min_key<32, false>(raw1, nvalid);
+            if (masked) drain_chunk<32, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<32, false>(raw1, nvalid, tbase, r0, r1);
             tmem_wait_ld_regs(raw0);
             tmem_ld32(taddr + 96, raw1);
-            m[2] = masked ? chunk_min_key<64, true>(raw0, nvalid) : chunk_min_key<64, false>(raw0, nvalid);
+            if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
             tmem_wait_ld_regs(raw1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-            m[3] = masked ? chunk_min_key<96, true>(raw1, nvalid) : chunk_min_key<96, false>(raw1, nvalid);
-#pragma unroll
-            for (int c = 0; c < NCH; c++) offer(__fadd_rn(m[c], tbase), r0, r1);
+            if (masked) drain_chunk<96, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<96, false>(raw1, nvalid, tbase, r0, r1);
         }
         if (q < n1) {
             // biased key -> (distance << KNN_IDX_BITS | index); a part that saw fewer than two chunks reports the
@@ -261,36 +261,39 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
 }
 
-// One warp per query: merge the column parts, then settle the one case the drain leaves open — a second
-// nearest neighbour inside the best's own 32-column chunk — by evaluating that chunk's other 31 distances
+// Eight lanes per query: merge the column parts, then settle the one case the drain leaves open — a second
+// nearest neighbour inside the best's own 8-column group — by evaluating that group's other 7 distances
 // with XOR + POPC on the original descriptors. out[p][q] = final (best, second) keys.
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
                                                      size_t stride_words, uint32_t n1, uint32_t n2,
                                                      const uint2 *__restrict__ part, uint2 *__restrict__ out) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), p = blockIdx.y;
-    if (q >= n1) return;
-    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+    static_assert(TC_GROUP == 8, "eight lanes per query");
+    const uint32_t sub = threadIdx.x & 7;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3), p = blockIdx.y;
+    const bool live = q < n1;
+    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu, key = 0xffffffffu;
+    if (live) {
 #pragma unroll
-    for (int s = 0; s < TC_COLSPLIT; s++) {
-        const uint2 v = part[((size_t)p * TC_COLSPLIT + s) * n1 + q];
-        const uint32_t lo = min(k1, v.x), hi = max(k1, v.x);   // v.x < v.y and k1 < k2
-        k2 = min(min(k2, v.y), hi);
-        k1 = lo;
+        for (int s = 0; s < TC_COLSPLIT; s++) {
+            const uint2 v = part[((size_t)p * TC_COLSPLIT + s) * n1 + q];
+            const uint32_t lo = min(k1, v.x), hi = max(k1, v.x);   // v.x < v.y and k1 < k2
+            k2 = min(min(k2, v.y), hi);
+            k1 = lo;
+        }
+        const uint32_t i1 = k1 & KNN_IDX_MASK;
+        const uint32_t col = (i1 & ~7u) + sub;
+        if (col < n2 && col != i1) {
+            const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
+            const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
+            const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+            const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                               __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            key = (d << KNN_IDX_BITS) | col;
+        }
     }
-    const uint32_t i1 = k1 & KNN_IDX_MASK;
-    const uint32_t col = (i1 & ~31u) + lane;
-    uint32_t key = 0xffffffffu;
-    if (col < n2 && col != i1) {
-        const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
-        const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
-        const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
-        const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-                           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-        key = (d << KNN_IDX_BITS) | col;
-    }
-    key = __reduce_min_sync(0xffffffffu, key);
-    if (lane == 0) out[(size_t)p * n1 + q] = make_uint2(k1, min(k2, key));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (live && sub == 0) out[(size_t)p * n1 + q] = make_uint2(k1, min(k2, key));
 }
 
 static int make_map(CUtensorMap *m, const void *base, uint64_t rows) {
@@ -346,7 +349,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
-    k_knn2_tc_fix<<<dim3(div_up(n1, 8), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
+    k_knn2_tc_fix<<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
     ctx->prof_end("knnfix");
     ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
