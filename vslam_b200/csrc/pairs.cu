@@ -91,9 +91,16 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     if ((rc = ctx->ws_ensure(WS_RESULT, (size_t)P * sizeof(vb_pair_result)))) return rc;
     if (out_matches && (rc = ctx->ws_ensure(WS_OUTMATCH, (size_t)P * k * 8))) return rc;
     // Software pipeline over sub-batches: the upload of batch b+1 and the download of batch b-1 run on two
-    // copy streams while batch b computes (they only overlap when the caller's buffers are pinned).
-    const uint32_t SB = (P >= 512) ? 256 : P;
-    const uint32_t nb = div_up(P, SB);
+    // copy streams while batch b computes (they only overlap when the caller's buffers are pinned). The first
+    // batch is small because its upload is the one nothing hides.
+    std::vector<uint32_t> cut;   // cut[b] .. cut[b+1] = pairs of sub-batch b
+    cut.push_back(0);
+    if (P >= 512) {
+        cut.push_back(64);
+        while (P - cut.back() > 320) cut.push_back(cut.back() + 256);
+    }
+    cut.push_back(P);
+    const uint32_t nb = (uint32_t)cut.size() - 1;
     if (!ctx->copy_in) {
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
@@ -113,8 +120,8 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     VB_CUDA(cudaEventRecord(ev_prev, ctx->stream));
     VB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_prev, 0));
     for (uint32_t b = 0; b < nb; b++) {
-        const uint32_t f0 = b == 0 ? 0 : b * SB + 1;                       // first frame not yet uploaded
-        const uint32_t f1 = (b + 1 == nb) ? nframes : (b + 1) * SB + 1;    // one past the halo frame
+        const uint32_t f0 = b == 0 ? 0 : cut[b] + 1;   // first frame not yet uploaded
+        const uint32_t f1 = cut[b + 1] + 1;            // one past the halo frame
         VB_CUDA(cudaMemcpyAsync(pts_d + (size_t)f0 * k * 2, pts + (size_t)f0 * k * 2, (size_t)(f1 - f0) * k * 8,
                                 cudaMemcpyHostToDevice, ctx->copy_in));
         VB_CUDA(cudaMemcpyAsync(desc_d + (size_t)f0 * k * bytes, desc + (size_t)f0 * k * bytes, (size_t)(f1 - f0) * k * bytes,
@@ -124,7 +131,7 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     const float2 *pts2 = reinterpret_cast<const float2 *>(pts_d);
     const uint32_t *desc32 = reinterpret_cast<const uint32_t *>(desc_d);
     for (uint32_t b = 0; b < nb; b++) {
-        const uint32_t p0 = b * SB, pb = (P - p0 < SB) ? P - p0 : SB;
+        const uint32_t p0 = cut[b], pb = cut[b + 1] - cut[b];
         VB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[b], 0));
         rc = pairs_core(ctx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
                         desc32 + (size_t)(p0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + p0,
