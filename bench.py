@@ -350,6 +350,7 @@ def main():
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
         line["kdtree"] = kdtree_stage(ctx, torch, dev, pts, k)
+        line["search_by_projection"] = projection_stage(ctx, k, None if args.no_cpu_baseline else cpu_oracle())
         if args.sweep:
             line["score_sweep"] = score_sweep(ctx, torch, dev, peak)
         print(json.dumps(line), flush=True)
@@ -415,6 +416,35 @@ def kdtree_stage(ctx, torch, dev, pts, k):
                                      "as written because its comparator copies the point vector (src/KDTree.cpp:128)")
     except Exception as e:  # the checker is optional here
         res["reference_cpu_ms_1core"] = f"unavailable: {e}"
+    return res
+
+
+def projection_stage(ctx, k, orc):
+    """SURVEY 8f rank 1 (not part of the pairs/s metric): search by projection of a 20 000-point map into one frame of k
+    keypoints (reference src/vslam.cpp:129-161) through the host-pointer C-ABI call, next to the oracle on one host core."""
+    from vslam_b200 import synth
+    n_map = 20000
+    s = synth.projection_scene(n_map, k, 77)
+    tree = ctx.kdtree_build(s["pts"])
+    run = lambda: ctx.search_by_projection(tree, s["X"], s["c2"], 1280, 720, s["desc"], s["ids"], s["obs_off"], s["obs_desc"])
+    for _ in range(3):
+        run()
+    ctx.profile(True)
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        g = run()
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    dev_ms = ctx.profile_ms("sbp")
+    ctx.profile(False)
+    tree.free()
+    res = {"map_points": n_map, "keypoints": k, "claimed": int(g[4]), "in_view": int(g[3].sum()),
+           "gpu_ms_host_call": e2e_ms, "gpu_ms_device": dev_ms, "map_points_per_s_host_call": n_map / (e2e_ms * 1e-3)}
+    if orc is not None:
+        t0 = time.perf_counter()
+        o = orc.search_by_projection(s["X"], s["c2"], 1280, 720, s["pts"], s["desc"], s["ids"], s["obs_off"], s["obs_desc"])
+        res["cpu_oracle_ms_1core"] = (time.perf_counter() - t0) * 1e3
+        res["matches_oracle"] = bool(np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]))
     return res
 
 

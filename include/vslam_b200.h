@@ -175,6 +175,27 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
                    uint32_t bytes, const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d);
 
 /* ------------------------------------------------------------------------------------------------
+ * Search by projection — replaces the loop at reference src/vslam.cpp:129-161 together with orb_distance
+ * (src/PointMap.cpp:36-46); the sole production caller of radius_search.
+ *   tree            kd-tree of the current frame's keypoints (vb_kdtree_build on frame.points, src/Frame.cpp:76)
+ *   map_points      [n][4] rows of pm.points (homogeneous), camera = c2 = K * R_t.rowRange(0,3), row-major 3x4
+ *   width, height   image size of the in-image test (:141)
+ *   frame_desc      [tree size][bytes] descriptors of the frame's keypoints
+ *   map_point_ids   [tree size] frame.map_point_ids, in/out: >= 0 means already claimed (:151); claims are written back
+ *   obs_offsets     [n+1] CSR over obs_desc: rows obs_offsets[i] .. obs_offsets[i+1] are the descriptors of map
+ *                   point i's observations (pm.frames[frame_ids[i][j]].descriptors.row(frame_point_ids[i][j]))
+ *   radius, dist_threshold   2 and DISTANCE_THRESHOLD = 64 in the reference (:149, :39)
+ *   assign          [n] out: keypoint index claimed by map point i, or -1 (the caller appends frame.id / idx to
+ *                   pm.frame_ids[i] / pm.frame_point_ids[i] for those, :155-156)
+ *   proj_xy [n][2], in_view [n]   optional outputs of the projection step (may be NULL)
+ * Result equals the reference's sequential first-unclaimed-wins loop exactly (map points in index order).
+ * ---------------------------------------------------------------------------------------------- */
+int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points, uint32_t n, const float *camera,
+                            int width, int height, const uint8_t *frame_desc, uint32_t bytes, int32_t *map_point_ids,
+                            const uint32_t *obs_offsets, const uint8_t *obs_desc, float radius, uint32_t dist_threshold,
+                            int32_t *assign, float *proj_xy, uint8_t *in_view, uint32_t *n_claimed);
+
+/* ------------------------------------------------------------------------------------------------
  * Timing hook for bench.py: CUDA-event time (ms) of the kernels of one class recorded on the context's
  * stream during the last call, keyed by name ("score", "hamming", "solve", ...). Returns <0 if unknown.
  * ---------------------------------------------------------------------------------------------- */

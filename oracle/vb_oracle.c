@@ -551,6 +551,75 @@ uint32_t vbo_orb_distance(const uint8_t *desc, const uint8_t *obs, int k, int by
     return mn;
 }
 
+/* Projection of homogeneous map points by a 3x4 camera, as cv::Mat `points * c2.t()` evaluates it
+ * (src/vslam.cpp:131; MatExpr -> cv::gemm(points, c2, 1, noArray(), 0, GEMM_2_T)). Observed on cv2 4.13.0
+ * (tests/golden, `projection_*`): fewer than 100 rows take OpenCV's own kernel — products and sums in
+ * double, one rounding to float; 100 rows or more are handed to the BLAS sgemm, which here evaluates
+ * ((x0*c0 + x1*c1) + x2*c2) + x3*c3 in fp32, one rounding per operation. */
+void vbo_project_points(const float *X, int n, const float *c2, float *out3) {
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 3; j++) {
+            const float *x = X + (size_t)i * 4, *c = c2 + (size_t)j * 4;
+            float r;
+            if (n < 100) {
+                double acc = (double)x[0] * (double)c[0];
+                acc += (double)x[1] * (double)c[1];
+                acc += (double)x[2] * (double)c[2];
+                acc += (double)x[3] * (double)c[3];
+                r = (float)acc;
+            } else {
+                float acc = x[0] * c[0];
+                acc = acc + x[1] * c[1];
+                acc = acc + x[2] * c[2];
+                acc = acc + x[3] * c[3];
+                r = acc;
+            }
+            out3[(size_t)i * 3 + j] = r;
+        }
+}
+
+/* src/vslam.cpp:129-161. Returns the number of map points that claimed a frame keypoint. */
+int vbo_search_by_projection(const float *X, int n, const float *c2, int W, int H, const float *pts,
+                             const int32_t *pre_idx, int k, const uint8_t *desc, int bytes,
+                             int32_t *map_point_ids, const int32_t *obs_off, const uint8_t *obs_desc,
+                             float radius, uint32_t dist_thr, int32_t *assign, float *proj_xy,
+                             uint8_t *in_view) {
+    float *pr = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
+    int32_t *hits = (int32_t *)malloc(sizeof(int32_t) * (size_t)(k > 0 ? k : 1));
+    vbo_project_points(X, n, c2, pr); /* :131 */
+    int claimed = 0;
+    for (int i = 0; i < n; i++) { /* :136-145: make non homogeneous, in-image test */
+        const float h = pr[3 * i + 2];
+        pr[3 * i + 0] = pr[3 * i + 0] / h;
+        pr[3 * i + 1] = pr[3 * i + 1] / h;
+        const float x = pr[3 * i + 0], y = pr[3 * i + 1];
+        const int in = (x >= 0 && x < (float)W && y >= 0 && y < (float)H) ? 1 : 0;
+        if (in_view) in_view[i] = (uint8_t)in;
+        if (proj_xy) { proj_xy[2 * i] = x; proj_xy[2 * i + 1] = y; }
+        assign[i] = -1;
+    }
+    for (int i = 0; i < n; i++) { /* :147-160 */
+        const float x = pr[3 * i + 0], y = pr[3 * i + 1];
+        if (!(x >= 0 && x < (float)W && y >= 0 && y < (float)H)) continue;
+        const int nh = vbo_kdtree_radius(pts, pre_idx, k, x, y, radius, hits, k); /* :149, pre-order */
+        for (int t = 0; t < nh; t++) {
+            const int idx = hits[t];
+            if (map_point_ids[idx] >= 0) continue; /* :151 */
+            const uint32_t d = vbo_orb_distance(desc + (size_t)idx * bytes, obs_desc + (size_t)obs_off[i] * bytes,
+                                                obs_off[i + 1] - obs_off[i], bytes); /* :152 */
+            if (d < dist_thr) { /* :153 */
+                map_point_ids[idx] = i;
+                assign[i] = idx;
+                claimed++;
+                break;
+            }
+        }
+    }
+    free(pr);
+    free(hits);
+    return claimed;
+}
+
 /* ============================ seed hook ======================================================= */
 
 static unsigned g_ref_seed = 0;

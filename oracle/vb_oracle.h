@@ -9,6 +9,7 @@
  *   matcher        src/Frame.cpp:82-105 (BFMatcher NORM_HAMMING knnMatch k=2, ratio 0.7, inlier copy-out)
  *   RansacFilter   src/RansacFilter.cpp:6-34 (sample sets), :36-67 (loop + best model),
  *                  :69-103 (8-point), :105-140 (residual / inliers / score)
+ *   search by projection   src/vslam.cpp:129-161, src/PointMap.cpp:36-46 (orb_distance)
  *
  * Pinning status (see DESIGN.md "Oracle"):
  *   - KD-tree: pinned against the reference's own src/KDTree.cpp compiled unmodified
@@ -120,6 +121,20 @@ int vbo_kdtree_radius(const float *pts, const int32_t *pre_idx, int n, float qx,
 /* ---- "next" rows ---------------------------------------------------------------- */
 /* src/PointMap.cpp:36-46 orb_distance: min Hamming distance between desc and each of k observations. */
 uint32_t vbo_orb_distance(const uint8_t *desc, const uint8_t *obs, int k, int bytes);
+/* src/vslam.cpp:131: X [n][4] homogeneous map points times c2^T (c2 = 3x4 camera, row-major) -> out3 [n][3],
+ * in the arithmetic cv::gemm uses for that shape (pinned against cv2 4.13 goldens; see the .c file). */
+void vbo_project_points(const float *X, int n, const float *c2, float *out3);
+/* src/vslam.cpp:129-161 search by projection: project every map point, keep those that land inside the W x H
+ * image, radius_search(r) the frame's kd-tree (pts [k][2], pre_idx from vbo_kdtree_build) around each, and let the
+ * map point claim the first hit (pre-order) that is still free (map_point_ids[idx] < 0) and whose orb_distance
+ * to the point's observations (obs_desc rows obs_off[i] .. obs_off[i+1]) is < dist_thr. Map points are processed
+ * in index order; a claimed keypoint is no longer free for later ones. assign[i] = claimed keypoint or -1;
+ * map_point_ids is updated in place; proj_xy [n][2] / in_view [n] are optional outputs. Returns the claim count. */
+int vbo_search_by_projection(const float *X, int n, const float *c2, int W, int H, const float *pts,
+                             const int32_t *pre_idx, int k, const uint8_t *desc, int bytes,
+                             int32_t *map_point_ids, const int32_t *obs_off, const uint8_t *obs_desc,
+                             float radius, uint32_t dist_thr, int32_t *assign, float *proj_xy,
+                             uint8_t *in_view);
 
 /* ---- seed hook consumed by the cvlite random_device stand-in (oracle/_ref builds only) -------- */
 void vbo_ref_seed_set(unsigned seed);

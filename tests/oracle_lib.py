@@ -74,6 +74,10 @@ class Oracle:
         L.vbo_kdtree_radius.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_float, C.c_float, _i32p, C.c_int]
         L.vbo_orb_distance.restype = C.c_uint32
         L.vbo_orb_distance.argtypes = [_u8p, _u8p, C.c_int, C.c_int]
+        L.vbo_project_points.argtypes = [_f32p, C.c_int, _f32p, _f32p]
+        L.vbo_search_by_projection.restype = C.c_int
+        L.vbo_search_by_projection.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _f32p, _i32p, C.c_int, _u8p, C.c_int,
+                                               _i32p, _i32p, _u8p, C.c_float, C.c_uint32, _i32p, _f32p, _u8p]
         L.vbo_pairs_run.restype = C.c_long
         L.vbo_pairs_run.argtypes = [_f32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float,
                                     C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -152,6 +156,30 @@ class Oracle:
         out = np.zeros((max(len(d1), 1), 2), np.int32)
         m = self.lib.vbo_match_l2f(d1, len(d1), d2, len(d2), d1.shape[1], ratio, out)
         return out[:m].copy()
+
+    # --- search by projection (src/vslam.cpp:129-161) ---
+    def project_points(self, X, c2):
+        X, c2 = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(c2, np.float32)
+        out = np.zeros((len(X), 3), np.float32)
+        self.lib.vbo_project_points(X, len(X), c2, out)
+        return out
+
+    def search_by_projection(self, X, c2, W, H, pts, desc, map_point_ids, obs_off, obs_desc, radius=2.0, dist_thr=64):
+        """Returns (assign [n], map_point_ids after, proj_xy [n][2], in_view [n])."""
+        X, c2 = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(c2, np.float32)
+        pts, desc = np.ascontiguousarray(pts, np.float32), np.ascontiguousarray(desc, np.uint8)
+        pre = self.kdtree_build(pts)
+        ids = np.ascontiguousarray(map_point_ids, np.int32).copy()
+        obs_off = np.ascontiguousarray(obs_off, np.int32)
+        obs_desc = np.ascontiguousarray(obs_desc, np.uint8).reshape(-1, desc.shape[1])
+        if len(obs_desc) == 0:
+            obs_desc = np.zeros((1, desc.shape[1]), np.uint8)
+        n = len(X)
+        assign, xy, inv = np.zeros(max(n, 1), np.int32), np.zeros((max(n, 1), 2), np.float32), np.zeros(max(n, 1), np.uint8)
+        self.lib.vbo_search_by_projection(X, n, c2, W, H, pts, pre, len(pts), desc, desc.shape[1], ids, obs_off, obs_desc,
+                                          radius, dist_thr, assign, xy, inv)
+        return assign[:n], ids, xy[:n], inv[:n]
+
 
     def match_features(self, p1, d1, p2, d2, ratio, min_items, iters, thr, seed):
         out = np.zeros((max(len(d1), 1), 2), np.int32)

@@ -112,3 +112,20 @@ def test_score_sum_blocked_order(oracle):
         assert oracle.score_sum(e) == tot
         if n:
             assert abs(tot - float(np.sum(e.astype(np.float64)))) <= 1e-12 * tot
+
+
+def test_projection_bit_exact_vs_cv2(oracle):
+    """points * c2.t() (src/vslam.cpp:131) on both sides of OpenCV's 100-row small-matrix threshold, and K * R_t."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "projection_cv2_4_13.npz"))
+    f = np.float32
+    for tag in ("n1", "n7", "n99", "n100", "n101", "n640", "n5000"):
+        X, c2, P = g[f"{tag}_X"], g[f"{tag}_c2"], g[f"{tag}_P"]
+        assert np.array_equal(_bits(oracle.project_points(X, c2)), _bits(P)), tag
+        # c2 = K * R_t.rowRange(0, 3): 3x3 times 3x4 without flags takes the fp32 small-matrix rule of test_gemm3_rule
+        K, Rt = g["K"], g[f"{tag}_Rt"]
+        r = np.empty((3, 4), f)
+        for i in range(3):
+            for j in range(4):
+                r[i, j] = f(f(f(K[i, 0] * Rt[0, j]) + f(K[i, 1] * Rt[1, j])) + f(K[i, 2] * Rt[2, j]))
+        assert np.array_equal(_bits(r), _bits(c2)), tag

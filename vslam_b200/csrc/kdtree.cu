@@ -433,6 +433,42 @@ static int tree_alloc(vb_ctx *ctx, uint32_t n, vb_tree **out) {
 
 using namespace vb;
 
+namespace vb {
+// Internal CSR radius search for callers inside the library (search by projection): offsets land in WS_OUT0
+// ([nq+1]), hit indices (original point indices, DFS pre-order per query) in WS_OUT1.
+int kd_radius_ws(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint64_t *total_out) {
+    vb_ctx *ctx = t->ctx;
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_OFFS, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT0, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_MISC, 64))) return rc;
+    uint32_t *counts = ctx->ws[WS_OFFS].as<uint32_t>();
+    uint32_t *offs = ctx->ws[WS_OUT0].as<uint32_t>();
+    unsigned long long *total_d = ctx->ws[WS_MISC].as<unsigned long long>();
+    ctx->prof_begin("kd_radius");
+    if (nq)
+        k_kd_radius<false><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q_d, nq, radius,
+                                                                                      counts, nullptr, nullptr);
+    k_scan_u32<<<1, 1024, 0, ctx->stream>>>(counts, nq, offs, total_d);
+    ctx->launches += nq ? 2 : 1;
+    VB_CUDA(cudaGetLastError());
+    unsigned long long total = 0;
+    VB_CUDA(cudaMemcpyAsync(&total, total_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *total_out = total;
+    if (total > 0xffffffffull) { set_error("radius result too large for 32-bit CSR offsets"); return VB_ERR_CAPACITY; }
+    if ((rc = ctx->ws_ensure(WS_OUT1, (size_t)(total ? total : 1) * 4))) return rc;
+    if (total && nq) {
+        k_kd_radius<true><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q_d, nq, radius,
+                                                                                     nullptr, offs, ctx->ws[WS_OUT1].as<uint32_t>());
+        ctx->launches++;
+        VB_CUDA(cudaGetLastError());
+    }
+    ctx->prof_end("kd_radius");
+    return VB_OK;
+}
+}  // namespace vb
+
 extern "C" {
 
 int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_d, uint32_t n, vb_tree **out) {

@@ -43,7 +43,7 @@ EXPORTS = [
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
-    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_profile_enable", "vb_profile_last_ms",
+    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_search_by_projection", "vb_profile_enable", "vb_profile_last_ms",
 ]
 
 
@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
     L.vb_match_features.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, C.POINTER(PairResult)]
     L.vb_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
+    L.vb_search_by_projection.argtypes = [vp, vp, vp, u32, vp, C.c_int, C.c_int, vp, u32, vp, vp, vp, f32, u32, vp, vp, vp,
+                                          C.POINTER(u32)]
     L.vb_profile_enable.argtypes = [vp, C.c_int]
     L.vb_profile_last_ms.restype = f32
     L.vb_profile_last_ms.argtypes = [vp, C.c_char_p]
@@ -187,6 +189,22 @@ class Context:
         out, m = np.zeros((max(len(d1), 1), 2), np.int32), C.c_uint32()
         self._chk(self.L.vb_match_l2f(self.h, _ptr(d1), len(d1), _ptr(d2), len(d2), d1.shape[1], ratio, _ptr(out), C.byref(m)))
         return out[:m.value].copy()
+
+    # ---- search by projection (reference src/vslam.cpp:129-161) ----
+    def search_by_projection(self, tree, X, c2, W, H, desc, map_point_ids, obs_off, obs_desc, radius=2.0, dist_thr=64):
+        """Returns (assign [n], map_point_ids after, proj_xy [n][2], in_view [n], n_claimed)."""
+        X, c2 = _f32(X), _f32(c2)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        ids = np.ascontiguousarray(map_point_ids, np.int32).copy()
+        obs_off = np.ascontiguousarray(obs_off, np.uint32)
+        obs_desc = np.ascontiguousarray(obs_desc, np.uint8)
+        n = len(X)
+        assign = np.zeros(max(n, 1), np.int32)
+        xy, inv, cnt = np.zeros((max(n, 1), 2), np.float32), np.zeros(max(n, 1), np.uint8), C.c_uint32()
+        self._chk(self.L.vb_search_by_projection(self.h, tree.h, _ptr(X), n, _ptr(c2), int(W), int(H), _ptr(desc),
+                                                 desc.shape[1], _ptr(ids), _ptr(obs_off), _ptr(obs_desc), float(radius),
+                                                 int(dist_thr), _ptr(assign), _ptr(xy), _ptr(inv), C.byref(cnt)))
+        return assign[:n], ids, xy[:n], inv[:n], cnt.value
 
     # ---- ransac ----
     def ransac_fundamental(self, p1, p2, matches, min_items=8, iters=100, thr=10.0, seed=0):

@@ -154,3 +154,55 @@ def correspondences(m: int, seed: int, outlier_frac: float = 0.3):
     """Config C5: m correspondences as float32 [m,4] rows (x1,y1,x2,y2) from the C1 generator."""
     fp = frame_pair(m, seed, outlier_frac=outlier_frac, nbytes=1, shuffle=False)
     return np.ascontiguousarray(np.concatenate([fp["p1"], fp["p2"]], 1), np.float32)
+
+
+def projection_scene(n_map: int, k: int, seed: int, nbytes: int = 32, contested: float = 0.3, claimed: float = 0.1):
+    """A map + current frame for search by projection (reference src/vslam.cpp:129-161).
+
+    k frame keypoints (a tenth of them in tight clusters, so radius-2 searches return several candidates), n_map
+    homogeneous map points: most project within ~1.5 px of a keypoint — `contested` of them onto a keypoint some other
+    map point also targets — the rest land elsewhere, outside the image or behind the camera. Every map point has 1-4
+    observation descriptors: bit-flipped copies of its target keypoint's descriptor (orb_distance well below 64) or,
+    for a fifth of them, unrelated ones. `claimed` of the keypoints already carry a map point id.
+    Returns dict(X [n][4], c2 [3][4], pts [k][2], desc [k][nbytes], ids [k], obs_off [n+1], obs_desc [*][nbytes]).
+    """
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    pts = np.stack([rng.uniform(2, W - 2, k), rng.uniform(2, H - 2, k)], 1)
+    nclu = k // 10
+    if nclu:   # clusters: copies of other keypoints displaced by < 1.5 px
+        src = rng.integers(nclu, k, nclu)
+        pts[:nclu] = pts[src] + rng.uniform(-1.0, 1.0, (nclu, 2))
+    pts = pts.astype(f32)
+    desc = random_descriptors(rng, k, nbytes)
+    R, t = default_motion(rng)
+    K = np.array([[FOCAL, 0, CX], [0, FOCAL, CY], [0, 0, 1.0]])
+    c2 = (K @ np.concatenate([R, t[:, None]], 1)).astype(f32)
+    target = rng.integers(0, k, n_map)
+    ncont = int(contested * n_map)
+    if ncont and n_map > ncont:
+        target[:ncont] = target[rng.integers(ncont, n_map, ncont)]
+    perm = rng.permutation(n_map)
+    target = target[perm]
+    uv = pts[target].astype(np.float64) + rng.uniform(-1.4, 1.4, (n_map, 2))
+    depth = rng.uniform(3.0, 12.0, n_map)
+    kind = rng.uniform(0, 1, n_map)
+    uv[kind < 0.10] += rng.uniform(20, 60, (int((kind < 0.10).sum()), 2))        # lands on nothing
+    uv[(kind >= 0.10) & (kind < 0.15)] += np.array([W, H])                         # outside the image
+    depth[(kind >= 0.15) & (kind < 0.18)] *= -1.0                                  # behind the camera
+    xc = np.stack([(uv[:, 0] - CX) / FOCAL * depth, (uv[:, 1] - CY) / FOCAL * depth, depth], 1)
+    xw = (xc - t) @ R          # R^T (xc - t)
+    X = np.concatenate([xw, np.ones((n_map, 1))], 1).astype(f32)
+    X[rng.integers(0, n_map, max(1, n_map // 50))] *= f32(1.5)                     # homogeneous scale != 1
+    nobs = rng.integers(1, 5, n_map)
+    obs_off = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    obs_desc = np.zeros((int(obs_off[-1]), nbytes), np.uint8)
+    unrelated = rng.uniform(0, 1, n_map) < 0.2
+    for i in range(n_map):
+        for o in range(obs_off[i], obs_off[i + 1]):
+            obs_desc[o] = random_descriptors(rng, 1, nbytes)[0] if unrelated[i] else \
+                flip_bits(rng, desc[target[i]][None, :], 40)[0]
+    ids = np.full(k, -1, np.int32)
+    pre = rng.choice(k, int(claimed * k), replace=False)
+    ids[pre] = rng.integers(0, max(n_map, 1), len(pre))
+    return {"X": X, "c2": c2, "pts": pts, "desc": desc, "ids": ids, "obs_off": obs_off, "obs_desc": obs_desc}
