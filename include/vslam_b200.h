@@ -196,6 +196,18 @@ int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points,
                             int32_t *assign, float *proj_xy, uint8_t *in_view, uint32_t *n_claimed);
 
 /* ------------------------------------------------------------------------------------------------
+ * Downstream of F.
+ * vb_extract_rt  — reference extract_Rt, src/helpers.cpp:3-35, for P fundamental matrices at once (F [P][9] row-major,
+ *   K [9]): R [P][9], t [P][3]; E_out [P][9] (optional) receives E = K^T F K, which is bit-identical to the two
+ *   cv::gemm calls of :4. The SVD of :7 is this build's fp64 Jacobi (as in the 8-point solve), not an OpenCV build's.
+ * vb_triangulate — reference triangulate, src/helpers.cpp:37-80: p1, p2 [n][2] matched keypoints, c1, c2 3x4 cameras
+ *   (row-major), points4 [n][4] = (X/w, Y/w, Z/w, 1) as at :71-74.
+ * ---------------------------------------------------------------------------------------------- */
+int vb_extract_rt(vb_ctx *ctx, const float *F, uint32_t P, const float *K, float *R, float *t, float *E_out);
+int vb_triangulate(vb_ctx *ctx, const float *p1, const float *p2, uint32_t n, const float *c1, const float *c2,
+                   float *points4);
+
+/* ------------------------------------------------------------------------------------------------
  * Timing hook for bench.py: CUDA-event time (ms) of the kernels of one class recorded on the context's
  * stream during the last call, keyed by name ("score", "hamming", "solve", ...). Returns <0 if unknown.
  * ---------------------------------------------------------------------------------------------- */

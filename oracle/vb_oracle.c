@@ -620,6 +620,117 @@ int vbo_search_by_projection(const float *X, int n, const float *c2, int W, int 
     return claimed;
 }
 
+/* ---- pose recovery and triangulation (src/helpers.cpp) ------------------------------------- */
+
+/* E = K.t() * F * K (src/helpers.cpp:4): cv::gemm(K, F, GEMM_1_T) — products and sums in double, one rounding — then
+ * a flag-free 3x3 product in the fp32 small-matrix order. Both pinned against cv2 (tests/golden). */
+void vbo_essential(const float *F, const float *K, float *E) {
+    float T[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double acc = (double)K[0 * 3 + i] * (double)F[0 * 3 + j];
+            acc += (double)K[1 * 3 + i] * (double)F[1 * 3 + j];
+            acc += (double)K[2 * 3 + i] * (double)F[2 * 3 + j];
+            T[i * 3 + j] = (float)acc;
+        }
+    mat3_mul_f32(T, K, E);
+}
+
+static float det3_f32(const float *m) { /* only its sign is used (:20,25) */
+    double d = (double)m[0] * ((double)m[4] * m[8] - (double)m[5] * m[7]) -
+               (double)m[1] * ((double)m[3] * m[8] - (double)m[5] * m[6]) +
+               (double)m[2] * ((double)m[3] * m[7] - (double)m[4] * m[6]);
+    return (float)d;
+}
+
+/* src/helpers.cpp:3-35. cv::SVD::compute is replaced by vbo_svd3x3 (defined sequence; PARITY UNPINNED there). */
+void vbo_extract_rt(const float *F, const float *K, float *R, float *t) {
+    float E[9], U[9], D[3], Vt[9];
+    vbo_essential(F, K, E);
+    vbo_svd3x3(E, U, D, Vt);                                   /* :7 */
+    for (int i = 0; i < 3; i++) t[i] = U[i * 3 + 2];           /* :9  U.col(2) */
+    const double nrm = sqrt(((double)t[0] * t[0] + (double)t[1] * t[1]) + (double)t[2] * t[2]); /* cv::norm: double */
+    const double inv = 1.0 / nrm;                              /* :11 Mat /= s scales by 1/s in double */
+    for (int i = 0; i < 3; i++) t[i] = (float)((double)t[i] * inv);
+    static const float Wm[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};   /* :13-16 */
+    static const float Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    float T[9], R1[9], R2[9];
+    mat3_mul_f32(U, Wm, T); mat3_mul_f32(T, Vt, R1);           /* :18 */
+    if (det3_f32(R1) < 0) for (int i = 0; i < 9; i++) R1[i] = -R1[i];
+    mat3_mul_f32(U, Wt, T); mat3_mul_f32(T, Vt, R2);           /* :23 */
+    if (det3_f32(R2) < 0) for (int i = 0; i < 9; i++) R2[i] = -R2[i];
+    const float tr = (R1[0] + R1[4]) + R1[8];                  /* :29 */
+    for (int i = 0; i < 9; i++) R[i] = (tr < 0) ? R2[i] : R1[i];
+    if (t[2] < 0) for (int i = 0; i < 3; i++) t[i] = -t[i];    /* :31-33 */
+}
+
+/* Right singular vector of the smallest singular value of a 4x4 (fp32 in, fp32 out): fp64 one-sided Jacobi over the
+ * column pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3), same rotation and stopping rule as vbo_svd3x3; ties keep the later
+ * column. Replaces cv::SVD::compute(A, ..., MODIFY_A | FULL_UV) + V_t.row(3) (src/helpers.cpp:57,67). */
+void vbo_null_vector_4x4(const float *A, float *v4) {
+    double G[4][4], V[4][4];
+    static const int PQ[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            G[i][j] = (double)A[i * 4 + j];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < VBO_SVD3_MAX_SWEEPS; sweep++) {
+        int rotated = 0;
+        for (int r = 0; r < 6; r++) {
+            int p = PQ[r][0], q = PQ[r][1];
+            double alpha = 0.0, bet = 0.0, gamma = 0.0;
+            for (int k = 0; k < 4; k++) {
+                alpha += G[k][p] * G[k][p];
+                bet += G[k][q] * G[k][q];
+                gamma += G[k][p] * G[k][q];
+            }
+            if (gamma == 0.0 || fabs(gamma) <= VBO_SVD3_EPS * sqrt(alpha * bet)) continue;
+            rotated = 1;
+            double zeta = (bet - alpha) / (2.0 * gamma);
+            double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            if (zeta < 0.0) t = -t;
+            double c = 1.0 / sqrt(1.0 + t * t);
+            double s = c * t;
+            for (int k = 0; k < 4; k++) {
+                double gp = G[k][p], gq = G[k][q];
+                G[k][p] = c * gp - s * gq;
+                G[k][q] = s * gp + c * gq;
+                double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - s * vq;
+                V[k][q] = s * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    int best = 0;
+    double bestn = 0.0;
+    for (int j = 0; j < 4; j++) {
+        double n2 = 0.0;
+        for (int k = 0; k < 4; k++) n2 += G[k][j] * G[k][j];
+        if (j == 0 || n2 <= bestn) { best = j; bestn = n2; }
+    }
+    for (int k = 0; k < 4; k++) v4[k] = (float)V[k][best];
+}
+
+/* src/helpers.cpp:37-80. p1, p2: [n][2]; c1, c2: 3x4 cameras; out: [n][4] = (X/w, Y/w, Z/w, 1). */
+void vbo_triangulate(const float *p1, const float *p2, int n, const float *c1, const float *c2, float *out) {
+    for (int i = 0; i < n; i++) {
+        float A[16], v[4];
+        for (int j = 0; j < 4; j++) { /* :49-52, one fp32 rounding per multiply and per subtract */
+            A[0 * 4 + j] = p1[2 * i] * c1[2 * 4 + j] - c1[0 * 4 + j];
+            A[1 * 4 + j] = p1[2 * i + 1] * c1[2 * 4 + j] - c1[1 * 4 + j];
+            A[2 * 4 + j] = p2[2 * i] * c2[2 * 4 + j] - c2[0 * 4 + j];
+            A[3 * 4 + j] = p2[2 * i + 1] * c2[2 * 4 + j] - c2[1 * 4 + j];
+        }
+        vbo_null_vector_4x4(A, v); /* :57,67 */
+        out[4 * i + 0] = v[0] / v[3]; /* :71-74 */
+        out[4 * i + 1] = v[1] / v[3];
+        out[4 * i + 2] = v[2] / v[3];
+        out[4 * i + 3] = 1.0f;
+    }
+}
+
 /* ============================ seed hook ======================================================= */
 
 static unsigned g_ref_seed = 0;

@@ -136,6 +136,14 @@ int vbo_search_by_projection(const float *X, int n, const float *c2, int W, int 
                              float radius, uint32_t dist_thr, int32_t *assign, float *proj_xy,
                              uint8_t *in_view);
 
+/* src/helpers.cpp:3-35 extract_Rt and :37-80 triangulate. E = K^T F K is pinned bit for bit
+ * against cv2; the SVDs (cv::SVD::compute, OpenCV-build dependent) are DEFINED here as fp64 one-sided Jacobi —
+ * PARITY UNPINNED for R, t and the triangulated points, which are checked against cv2 to a tolerance only. */
+void vbo_essential(const float *F, const float *K, float *E);
+void vbo_extract_rt(const float *F, const float *K, float *R, float *t);
+void vbo_null_vector_4x4(const float *A, float *v4);
+void vbo_triangulate(const float *p1, const float *p2, int n, const float *c1, const float *c2, float *out);
+
 /* ---- seed hook consumed by the cvlite random_device stand-in (oracle/_ref builds only) -------- */
 void vbo_ref_seed_set(unsigned seed);
 unsigned vbo_ref_seed_next(void);

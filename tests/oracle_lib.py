@@ -78,6 +78,10 @@ class Oracle:
         L.vbo_search_by_projection.restype = C.c_int
         L.vbo_search_by_projection.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _f32p, _i32p, C.c_int, _u8p, C.c_int,
                                                _i32p, _i32p, _u8p, C.c_float, C.c_uint32, _i32p, _f32p, _u8p]
+        L.vbo_essential.argtypes = [_f32p, _f32p, _f32p]
+        L.vbo_extract_rt.argtypes = [_f32p, _f32p, _f32p, _f32p]
+        L.vbo_null_vector_4x4.argtypes = [_f32p, _f32p]
+        L.vbo_triangulate.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]
         L.vbo_pairs_run.restype = C.c_long
         L.vbo_pairs_run.argtypes = [_f32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float,
                                     C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -156,6 +160,23 @@ class Oracle:
         out = np.zeros((max(len(d1), 1), 2), np.int32)
         m = self.lib.vbo_match_l2f(d1, len(d1), d2, len(d2), d1.shape[1], ratio, out)
         return out[:m].copy()
+
+    # --- downstream of F (src/helpers.cpp) ---
+    def essential(self, F, K):
+        E = np.zeros((3, 3), np.float32)
+        self.lib.vbo_essential(np.ascontiguousarray(F, np.float32), np.ascontiguousarray(K, np.float32), E)
+        return E
+
+    def extract_rt(self, F, K):
+        R, t = np.zeros((3, 3), np.float32), np.zeros(3, np.float32)
+        self.lib.vbo_extract_rt(np.ascontiguousarray(F, np.float32), np.ascontiguousarray(K, np.float32), R, t)
+        return R, t
+
+    def triangulate(self, p1, p2, c1, c2):
+        p1, p2 = np.ascontiguousarray(p1, np.float32), np.ascontiguousarray(p2, np.float32)
+        out = np.zeros((max(len(p1), 1), 4), np.float32)
+        self.lib.vbo_triangulate(p1, p2, len(p1), np.ascontiguousarray(c1, np.float32), np.ascontiguousarray(c2, np.float32), out)
+        return out[:len(p1)]
 
     # --- search by projection (src/vslam.cpp:129-161) ---
     def project_points(self, X, c2):

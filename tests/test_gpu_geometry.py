@@ -1,0 +1,53 @@
+"""extract_Rt / triangulate (reference src/helpers.cpp:3-80) through the C ABI vs the oracle: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geometry_cv2_4_13.npz"))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from vslam_b200.lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_extract_rt_bit_exact_vs_oracle_and_cv2_E(ctx, oracle):
+    rng = np.random.default_rng(3)
+    F = np.concatenate([G["F"], (rng.standard_normal((200, 3, 3)) * [1e-6, 1e-6, 1e-3]).astype(np.float32)])
+    R, t, E = ctx.extract_rt(F, G["K"])
+    assert np.array_equal(_bits(E[:len(G["E"])]), _bits(G["E"]))          # E = K^T F K: identical to cv::gemm's
+    for i in range(len(F)):
+        Ro, to = oracle.extract_rt(F[i], G["K"])
+        assert np.array_equal(_bits(R[i]), _bits(Ro)) and np.array_equal(_bits(t[i]), _bits(to)), i
+        assert np.array_equal(_bits(E[i]), _bits(oracle.essential(F[i], G["K"])))
+
+
+def test_extract_rt_on_pipeline_output(ctx, oracle):
+    """F as produced by the pair pipeline -> R, t close to the synthetic motion's direction."""
+    from vslam_b200 import synth
+    fp = synth.frame_pair(3000, 5)
+    res = ctx.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], ctx.params(0.7, 8, 512, 10.0, 4))
+    R, t, _ = ctx.extract_rt(res["F"], G["K"])
+    Ro, to = oracle.extract_rt(res["F"], G["K"])
+    assert np.array_equal(_bits(R[0]), _bits(Ro)) and np.array_equal(_bits(t[0]), _bits(to))
+    assert abs(np.linalg.det(R[0].astype(np.float64)) - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 400, 5000])
+def test_triangulate_bit_exact_vs_oracle(ctx, oracle, n):
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, len(G["tri_p1"]), n)
+    p1 = G["tri_p1"][idx] + rng.normal(0, 0.05, (n, 2)).astype(np.float32)
+    p2 = G["tri_p2"][idx] + rng.normal(0, 0.05, (n, 2)).astype(np.float32)
+    P = ctx.triangulate(p1, p2, G["tri_c1"], G["tri_c2"])
+    Po = oracle.triangulate(p1, p2, G["tri_c1"], G["tri_c2"])
+    assert np.array_equal(_bits(P), _bits(Po))

@@ -110,6 +110,7 @@ struct vb_ctx {
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];
     uint64_t launches = 0;
+    uint32_t func_attr_done = 0;   // per-context (hence per-device) bits: large-smem attribute set for kernel i
     bool profile = false;
     std::map<std::string, vb::ProfEntry> prof;
 

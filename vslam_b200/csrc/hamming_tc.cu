@@ -311,10 +311,9 @@ bool hamming_tc_eligible(const HammingPlan &pl) {
 // the latter, which k_knn2_finish reads as a single split.
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                       const uint2 **final_part) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        attr_set = true;
+        ctx->func_attr_done |= 1u;
     }
     const uint32_t P = pl.P, n1 = pl.n1, n2 = pl.n2;
     const bool seq = P > 1 && n1 == n2 && stride_words == (size_t)n1 * 8 && d2 == d1 + stride_words;

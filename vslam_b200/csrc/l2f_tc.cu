@@ -405,10 +405,10 @@ bool l2_tc_eligible(uint32_t n1, uint32_t n2, uint32_t dim) {
 template <int DIM>
 static int l2_tc_run(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, uint32_t n2, ulonglong2 *out) {
     using Cfg = LtCfg<DIM>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    constexpr uint32_t bit = DIM == 128 ? 2u : 4u;
+    if (!(ctx->func_attr_done & bit)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_l2_tc<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
+        ctx->func_attr_done |= bit;
     }
     int rc;
     const uint32_t ntiles = div_up(n2, LT_NCOLS), n2_pad = ntiles * LT_NCOLS, nct = ntiles * LT_CHUNKS;

@@ -43,7 +43,7 @@ EXPORTS = [
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
-    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_search_by_projection", "vb_profile_enable", "vb_profile_last_ms",
+    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms",
 ]
 
 
@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_search_by_projection.argtypes = [vp, vp, vp, u32, vp, C.c_int, C.c_int, vp, u32, vp, vp, vp, f32, u32, vp, vp, vp,
                                           C.POINTER(u32)]
+    L.vb_extract_rt.argtypes = [vp, vp, u32, vp, vp, vp, vp]
+    L.vb_triangulate.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.vb_profile_enable.argtypes = [vp, C.c_int]
     L.vb_profile_last_ms.restype = f32
     L.vb_profile_last_ms.argtypes = [vp, C.c_char_p]
@@ -205,6 +207,22 @@ class Context:
                                                  desc.shape[1], _ptr(ids), _ptr(obs_off), _ptr(obs_desc), float(radius),
                                                  int(dist_thr), _ptr(assign), _ptr(xy), _ptr(inv), C.byref(cnt)))
         return assign[:n], ids, xy[:n], inv[:n], cnt.value
+
+    # ---- downstream of F (reference src/helpers.cpp) ----
+    def extract_rt(self, F, K):
+        """F [P][3][3] (or [3][3]) -> (R [P][3][3], t [P][3], E [P][3][3])."""
+        F = _f32(F).reshape(-1, 9)
+        K = _f32(K).reshape(9)
+        P = len(F)
+        R, t, E = np.zeros((max(P, 1), 9), np.float32), np.zeros((max(P, 1), 3), np.float32), np.zeros((max(P, 1), 9), np.float32)
+        self._chk(self.L.vb_extract_rt(self.h, _ptr(F), P, _ptr(K), _ptr(R), _ptr(t), _ptr(E)))
+        return R[:P].reshape(-1, 3, 3), t[:P], E[:P].reshape(-1, 3, 3)
+
+    def triangulate(self, p1, p2, c1, c2):
+        p1, p2, c1, c2 = _f32(p1), _f32(p2), _f32(c1).reshape(12), _f32(c2).reshape(12)
+        out = np.zeros((max(len(p1), 1), 4), np.float32)
+        self._chk(self.L.vb_triangulate(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(c1), _ptr(c2), _ptr(out)))
+        return out[:len(p1)]
 
     # ---- ransac ----
     def ransac_fundamental(self, p1, p2, matches, min_items=8, iters=100, thr=10.0, seed=0):
