@@ -9,8 +9,9 @@
 // exact in the f32 accumulator), so a tile of 128 x 256 distances is 8 tcgen05.mma (K = 32 bytes each).
 //
 //   k_expand_pm1   descriptor bits -> e4m3 +-1 rows of 256 bytes (one pass, 16-byte stores).
-//   k_knn2_tc      CTA = 256 queries (two M = 128 accumulators of 256 columns = all 512 TMEM columns)
-//                  against the whole train set in 256-wide tiles.
+//   k_knn2_tc      persistent CTAs (one per SM) over work units; a unit = 256 queries of one pair (two M = 128
+//                  accumulators of 256 columns = all 512 TMEM columns) against that pair's whole train set in
+//                  256-wide tiles. Barriers, TMEM and the B ring carry over from unit to unit.
 //                    warp 0     TMA producer: A once (64 KB), B tiles (64 KB) through a 2-stage ring
 //                    warp 1     one thread issues the UMMAs: acc0 <- A0 * B^T, acc1 <- A1 * B^T per tile
 //                    warp 2     TMEM allocation / release
@@ -108,18 +109,20 @@ __device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[32], uint32_t 
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
-          uint32_t rowstride_q, uint32_t rowstride_t, uint2 *__restrict__ part, int dbg) {
+          uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
     const uint32_t sA = smem0;
     const uint32_t sB = smem0 + TC_A_BYTES;
     const uint32_t sBar = sB + 2 * TC_B_BYTES;
     const uint32_t bar_a = sBar, bar_full = sBar + 8, bar_empty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 56;
-    const uint32_t s_tmem = sBar + 72;
+    const uint32_t s_tmem = sBar + 72, bar_afree = sBar + 80;
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t p = blockIdx.y;
-    const uint32_t q0 = blockIdx.x * TC_QROWS;
+    // Persistent CTA: work units u = blockIdx.x, blockIdx.x + gridDim.x, ... with unit = (pair p, 256-query block).
+    // Barriers, TMEM and the B ring live across units; only A is reloaded (once the previous unit's last MMA has
+    // retired), so the per-unit cost is one exposed A load instead of a CTA launch + TMEM allocation + pipeline fill.
+    const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
     const uint32_t ntiles = (n2 + TC_NCOLS - 1) / TC_NCOLS;
 
     if (warp == 0 && lane == 0) {
@@ -128,6 +131,7 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
     if (warp == 1 && lane == 0) {
         mbar_init(bar_a, 1);
+        mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
@@ -145,112 +149,125 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 
     if (warp == 0) {
         if (lane == 0) {
-            const int32_t qrow = (int32_t)(p * rowstride_q + q0);
-            mbar_expect_tx(bar_a, TC_A_BYTES);
+            uint32_t g = 0, ul = 0;   // tiles / units issued so far by this CTA
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
+                const uint32_t p = u / qblocks, q0 = (u % qblocks) * TC_QROWS;
+                const int32_t qrow = (int32_t)(p * rowstride_q + q0);
+                mbar_wait(bar_afree, (ul & 1) ^ 1);   // the previous unit's MMAs no longer read A
+                mbar_expect_tx(bar_a, TC_A_BYTES);
 #pragma unroll
-            for (int h = 0; h < 2; h++)
+                for (int h = 0; h < 2; h++)
 #pragma unroll
-                for (int kk = 0; kk < 2; kk++)
-                    tma_load_2d(sA + (h * 2 + kk) * TC_BOX_BYTES, &map_q, kk * 128, qrow + h * 128, bar_a);
-            const int32_t trow = (int32_t)(p * rowstride_t);
-            for (uint32_t j = 0; j < ntiles; j++) {
-                const uint32_t s = j & 1, ph = (j >> 1) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                if ((dbg & 4) && j >= 2) {   // measurement only: reuse the resident stage, no L2 -> SM traffic
-                    mbar_arrive(bar_full + 8 * s);
-                    continue;
+                    for (int kk = 0; kk < 2; kk++)
+                        tma_load_2d(sA + (h * 2 + kk) * TC_BOX_BYTES, &map_q, kk * 128, qrow + h * 128, bar_a);
+                const int32_t trow = (int32_t)(p * rowstride_t);
+                for (uint32_t j = 0; j < ntiles; j++, g++) {
+                    const uint32_t s = g & 1, ph = (g >> 1) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    if ((dbg & 4) && g >= 2) {   // measurement only: reuse the resident stage, no L2 -> SM traffic
+                        mbar_arrive(bar_full + 8 * s);
+                        continue;
+                    }
+                    mbar_expect_tx(bar_full + 8 * s, TC_B_BYTES);
+                    const uint32_t dst = sB + s * TC_B_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+                        for (int r = 0; r < 2; r++)
+                            tma_load_2d(dst + (kk * 2 + r) * TC_BOX_BYTES, &map_t, kk * 128,
+                                        trow + (int32_t)(j * TC_NCOLS) + r * 128, bar_full + 8 * s);
                 }
-                mbar_expect_tx(bar_full + 8 * s, TC_B_BYTES);
-                const uint32_t dst = sB + s * TC_B_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 2; kk++)
-#pragma unroll
-                    for (int r = 0; r < 2; r++)
-                        tma_load_2d(dst + (kk * 2 + r) * TC_BOX_BYTES, &map_t, kk * 128,
-                                    trow + (int32_t)(j * TC_NCOLS) + r * 128, bar_full + 8 * s);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(UMMA_FMT_E4M3, 128, TC_NCOLS);
-            mbar_wait(bar_a, 0);
-            for (uint32_t j = 0; j < ntiles; j++) {
-                const uint32_t s = j & 1, ph = (j >> 1) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
+            uint32_t g = 0, ul = 0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
+                mbar_wait(bar_a, ul & 1);
                 tc_fence_after();
-                const uint32_t bbase = sB + s * TC_B_BYTES;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    mbar_wait(bar_tempty + 8 * h, (j & 1) ^ 1);   // accumulator h drained (tile j-1)
+                for (uint32_t j = 0; j < ntiles; j++, g++) {
+                    const uint32_t s = g & 1, ph = (g >> 1) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
+                    const uint32_t bbase = sB + s * TC_B_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < 2; kk++)
+                    for (int h = 0; h < 2; h++) {
+                        mbar_wait(bar_tempty + 8 * h, (g & 1) ^ 1);   // accumulator h drained (previous tile)
+                        tc_fence_after();
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint64_t ad = smem_desc_sw128(sA + (h * 2 + kk) * TC_BOX_BYTES + k * 32);
-                            const uint64_t bd = smem_desc_sw128(bbase + kk * 2 * TC_BOX_BYTES + k * 32);
-                            umma_f8f6f4(tmem_base + h * TC_NCOLS, ad, bd, idesc, (kk | k) != 0 ? 1u : 0u);
-                        }
-                    umma_commit(bar_tfull + 8 * h);
+                        for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const uint64_t ad = smem_desc_sw128(sA + (h * 2 + kk) * TC_BOX_BYTES + k * 32);
+                                const uint64_t bd = smem_desc_sw128(bbase + kk * 2 * TC_BOX_BYTES + k * 32);
+                                umma_f8f6f4(tmem_base + h * TC_NCOLS, ad, bd, idesc, (kk | k) != 0 ? 1u : 0u);
+                            }
+                        umma_commit(bar_tfull + 8 * h);
+                    }
+                    umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
                 }
-                umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
+                umma_commit(bar_afree);   // ... and every MMA of this unit has consumed A
             }
         }
     } else if (warp >= 4) {
         const uint32_t ew = warp - 4;
         const uint32_t quad = warp & 3, h = (ew >> 2) & 1, ch = ew >> 3;   // TMEM lane quadrant, accumulator, column part
         const uint32_t row = h * 128 + quad * 32 + lane;
-        const uint32_t q = q0 + row;
         constexpr uint32_t CW = TC_NCOLS / TC_COLSPLIT;
         constexpr int NCH = CW / 32;
         static_assert(NCH == 4, "the drain below is written out for four 32-column chunks per warp");
         const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + h * TC_NCOLS + ch * CW;
-        // running (best, best outside the best's chunk) as biased global keys
-        float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
-        float tbase = (float)(ch * CW) + TC_KEY_BIAS;   // key bias + first column of this warp's part of tile j
         uint32_t raw0[32], raw1[32];
-        for (uint32_t j = 0; j < ntiles; j++, tbase += (float)TC_NCOLS) {
-            mbar_wait(bar_tfull + 8 * h, j & 1);
-            tc_fence_after();
-            const uint32_t tile0 = j * TC_NCOLS + ch * CW;
-            if ((dbg & 2) || tile0 >= n2) {   // (dbg 2: MMA floor measurement) / nothing valid in this part of the last tile
+        uint32_t g = 0;   // tiles drained so far by this CTA (accumulator barrier phase)
+        for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + row;
+            // running (best, best outside the best's group) as biased global keys
+            float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
+            float tbase = (float)(ch * CW) + TC_KEY_BIAS;   // key bias + first column of this warp's part of tile j
+            for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)TC_NCOLS) {
+                mbar_wait(bar_tfull + 8 * h, g & 1);
+                tc_fence_after();
+                const uint32_t tile0 = j * TC_NCOLS + ch * CW;
+                if ((dbg & 2) || tile0 >= n2) {   // (dbg 2: MMA floor measurement) / nothing valid in this part of the last tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                    continue;
+                }
+                const bool masked = tile0 + CW > n2;
+                const uint32_t nvalid = n2 - tile0;
+                // chunk c+1 is in flight while chunk c is reduced; the accumulator goes back to the MMA warp as soon
+                // as its last chunk has landed in registers
+                tmem_ld32(taddr, raw0);
+                tmem_wait_ld_regs(raw0);
+                tmem_ld32(taddr + 32, raw1);
+                if (masked) drain_chunk<0, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<0, false>(raw0, nvalid, tbase, r0, r1);
+                tmem_wait_ld_regs(raw1);
+                tmem_ld32(taddr + 64, raw0);
+                if (masked) drain_chunk<32, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<32, false>(raw1, nvalid, tbase, r0, r1);
+                tmem_wait_ld_regs(raw0);
+                tmem_ld32(taddr + 96, raw1);
+                if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
+                tmem_wait_ld_regs(raw1);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-                continue;
+                if (masked) drain_chunk<96, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<96, false>(raw1, nvalid, tbase, r0, r1);
             }
-            const bool masked = tile0 + CW > n2;
-            const uint32_t nvalid = n2 - tile0;
-            // chunk c+1 is in flight while chunk c is reduced; the accumulator goes back to the MMA warp as soon
-            // as its last chunk has landed in registers
-            tmem_ld32(taddr, raw0);
-            tmem_wait_ld_regs(raw0);
-            tmem_ld32(taddr + 32, raw1);
-            if (masked) drain_chunk<0, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<0, false>(raw0, nvalid, tbase, r0, r1);
-            tmem_wait_ld_regs(raw1);
-            tmem_ld32(taddr + 64, raw0);
-            if (masked) drain_chunk<32, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<32, false>(raw1, nvalid, tbase, r0, r1);
-            tmem_wait_ld_regs(raw0);
-            tmem_ld32(taddr + 96, raw1);
-            if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
-            tmem_wait_ld_regs(raw1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-            if (masked) drain_chunk<96, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<96, false>(raw1, nvalid, tbase, r0, r1);
-        }
-        if (q < n1) {
-            // biased key -> (distance << KNN_IDX_BITS | index); a part that saw fewer than two chunks reports the
-            // largest key, which the merge ignores
-            uint32_t out[2];
-            const float ks[2] = {r0, r1};
+            if (q < n1) {
+                // biased key -> (distance << KNN_IDX_BITS | index); a part that saw fewer than two groups reports the
+                // largest key, which the merge ignores
+                uint32_t out[2];
+                const float ks[2] = {r0, r1};
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const uint32_t ki = __float2uint_rz(ks[i]);
-                out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
-                                            : 0xffffffffu;
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t ki = __float2uint_rz(ks[i]);
+                    out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                : 0xffffffffu;
+                }
+                part[((size_t)p * TC_COLSPLIT + ch) * n1 + q] = make_uint2(out[0], out[1]);
             }
-            part[((size_t)p * TC_COLSPLIT + ch) * n1 + q] = make_uint2(out[0], out[1]);
         }
     }
     tc_fence_before();
@@ -340,12 +357,13 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     CUtensorMap mq, mt;
     if ((rc = make_map(&mq, Eq, (uint64_t)P * n1))) return rc;
     if ((rc = make_map(&mt, Et, (uint64_t)P * n2))) return rc;
-    dim3 grid(div_up(n1, TC_QROWS), P);
+    const uint32_t nunits = div_up(n1, TC_QROWS) * P;
+    const uint32_t grid = nunits < (uint32_t)ctx->sm_count ? nunits : (uint32_t)ctx->sm_count;   // one persistent CTA per SM
     ctx->prof_begin("hamming");
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
     uint2 *fixed = part + (size_t)P * TC_COLSPLIT * n1;
     static const int dbg = getenv("VB_TC_DBG") ? atoi(getenv("VB_TC_DBG")) : 0;
-    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, part, dbg);
+    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
     k_knn2_tc_fix<<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
