@@ -67,20 +67,22 @@ __global__ void __launch_bounds__(256) k_expand_pm1(const uint32_t *__restrict__
 // 2^14 * (2 * distance - 256) + col: an integer of magnitude below 2^23, exact in fp32, whose order is
 // (distance, train index) — knnMatch's order including its lower-index-first ties. Keys are never equal.
 //
-// Per 32-column chunk a thread forms the 32 keys (one FADD each, immediate column operand, FMA pipe), reduces
-// every 8-column group to its minimum key with a 3-input min tree (4 FMNMX3/FMNMX, ALU pipe) and offers the four
-// group minima, two at a time, to its running (r0 <= r1). There is no branch, no vote and no data-dependent
-// work. What this yields per row is the best candidate and the best candidate OUTSIDE the best's own group; the
-// only thing it can miss is a second nearest neighbour that shares the best's 8-column group, which
-// k_knn2_tc_fix settles afterwards by evaluating those 7 distances directly (XOR + POPC on the original
-// descriptors). (One key per 32-column chunk costs 7 ALU instructions per chunk less here, but makes the fix
-// read 1 KB of descriptors per query: 0.78 ms per 1024 pairs against 0.2 ms.)
+// The drain works on 8-column groups. Per group a thread takes the largest of the 8 accumulator values with a
+// 3-input max tree (4 FMNMX3/FMNMX) and turns it into ONE key, (first column of the group) - 2^14 * (best dot of
+// the group), whose order is (best distance in the group, group position); the four group keys of a 32-column
+// chunk are offered, two at a time, to the row's running (r0 <= r1). No per-value work beyond the max tree, no
+// branch, no vote, nothing data-dependent. What this yields per row is the group holding the nearest neighbour
+// (equal distances resolve to the lower group, hence to the lower index) and the best OTHER group. The two
+// nearest neighbours lie in those two groups: the second one is either another member of the best's group or the
+// best member of the best other group. k_knn2_tc_fix evaluates those 16 distances directly (XOR + POPC on the
+// original descriptors) and takes their top-2 by (distance, index).
 constexpr int TC_KEY_SHIFT = 14;
 constexpr uint32_t TC_MAX_TRAIN = 1u << TC_KEY_SHIFT;
 constexpr float TC_KEY_BIAS = 4194304.f;   // 2^22 = 2^14 * 256: makes keys non-negative
 constexpr float TC_KEY_NONE = 3.0e7f;      // above every real key (< 2^24)
 
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // One 32-column chunk of one row: the four minimum keys of its 8-column groups go into the running (r0 <= r1).
 // Columns are counted from the start of the warp's column part (C0 = 32 * chunk); `base` makes them global.
@@ -90,21 +92,23 @@ __device__ __forceinline__ void offer2(float a, float b, float &r0, float &r1) {
     r1 = min3(r1, fmaxf(r0, lo), hi);
     r0 = fminf(r0, lo);
 }
-template <int C0, bool MASKED>
-__device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[32], uint32_t nvalid, float base, float &r0, float &r1) {
-    float g[4];
+template <int C0, bool MASKED, int NCOLS = 32>
+__device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[NCOLS], uint32_t nvalid, float base, float &r0, float &r1) {
+    static_assert(NCOLS == 32 || NCOLS == 16, "whole pairs of 8-column groups");
+    float g[NCOLS / 8];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float k[8];
+    for (int j = 0; j < NCOLS / 8; j++) {
+        float v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            k[i] = __fsub_rn((float)(C0 + 8 * j + i), __uint_as_float(raw[8 * j + i]));
-            if (MASKED) k[i] = (uint32_t)(C0 + 8 * j + i) < nvalid ? k[i] : TC_KEY_NONE;
+            v[i] = __uint_as_float(raw[8 * j + i]);
+            if (MASKED) v[i] = (uint32_t)(C0 + 8 * j + i) < nvalid ? v[i] : -TC_KEY_NONE;
         }
-        g[j] = __fadd_rn(fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), k[6]), k[7]), base);
+        const float vmax = fmaxf(max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), v[6]), v[7]);
+        g[j] = __fadd_rn(__fsub_rn((float)(C0 + 8 * j), vmax), base);   // group key: first column of the group - 2^14 * best dot
     }
-    offer2(g[0], g[1], r0, r1);
-    offer2(g[2], g[3], r0, r1);
+#pragma unroll
+    for (int j = 0; j < NCOLS / 8; j += 2) offer2(g[j], g[j + 1], r0, r1);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -278,18 +282,218 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
 }
 
-// Eight lanes per query: merge the column parts, then settle the one case the drain leaves open — a second
-// nearest neighbour inside the best's own 8-column group — by evaluating that group's other 7 distances
-// with XOR + POPC on the original descriptors. out[p][q] = final (best, second) keys.
+// ---- FP4 variant ---------------------------------------------------------------------------------------
+// Same algorithm with the descriptors expanded to packed e2m1 (+1 = 0x2, -1 = 0xA; 128 bytes per descriptor) and
+// block-scaled UMMAs (kind::mxf4, K = 64 per instruction: twice the fp8 rate, half the shared-memory and L2 bytes).
+// Every scale factor is the same ue8m0 value 2^7, for A and for B, so an accumulator still holds 2^14 * dot exactly
+// and the drain is unchanged; because the factors are all equal, their TMEM layout does not matter — a 32-column
+// strip of TMEM is simply filled with 0x86 bytes once per CTA. That strip costs accumulator width: two accumulators
+// of 240 columns (512 = 32 + 2 * 240), so a train tile is 240 descriptors.
+constexpr int T4_NCOLS = 240;                          // train descriptors per tile (UMMA N)
+constexpr int T4_STAGES = 4;                           // B ring depth
+constexpr int T4_ROWBYTES = 128;                       // expanded descriptor: 256 e2m1 values
+constexpr uint32_t T4_A_BYTES = 2 * 128 * T4_ROWBYTES;        // [half][128 rows][128 B]
+constexpr uint32_t T4_B_BYTES = T4_NCOLS * T4_ROWBYTES;       // [240 rows][128 B] = 30 atoms of 1 KB
+constexpr uint32_t T4_SF_COLS = 32;                    // TMEM columns [0, 32): scale factors
+constexpr uint32_t T4_SMEM_BYTES = T4_A_BYTES + T4_STAGES * T4_B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert(T4_B_BYTES % 1024 == 0, "stages must stay 1024-byte aligned for the 128-byte swizzle");
+
+__global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict__ src, size_t stride_words, uint32_t rows,
+                                                     uint32_t P, uint8_t *__restrict__ dst) {
+    // one thread = one 32-bit word of a descriptor -> 16 output bytes (two bits per byte, low nibble first)
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;   // word index within frame p = blockIdx.y
+    if (t >= rows * 8) return;
+    const uint32_t p = blockIdx.y;
+    const uint32_t w = __ldg(src + (size_t)p * stride_words + t);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t x = (w >> (8 * i)) & 0xffu;
+        const uint32_t sp = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;   // bits (2j, 2j+1) -> byte j, positions 0, 1
+        o[i] = 0x22222222u | ((sp & 0x01010101u) << 3) | ((sp & 0x02020202u) << 6);  // nibble 0x2 = +1.0, 0xA = -1.0
+    }
+    *reinterpret_cast<uint4 *>(dst + ((size_t)p * rows * 8 + t) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
+           uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem0;
+    const uint32_t sB = smem0 + T4_A_BYTES;
+    const uint32_t sBar = sB + T4_STAGES * T4_B_BYTES;
+    const uint32_t bar_a = sBar, bar_afree = sBar + 8, bar_tfull = sBar + 16, bar_tempty = sBar + 32, s_tmem = sBar + 48,
+                   bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
+    const uint32_t ntiles = (n2 + T4_NCOLS - 1) / T4_NCOLS;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_t);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_afree, 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4 * TC_COLSPLIT);   // one arrival per draining warp
+        }
+        for (int s = 0; s < T4_STAGES; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
+    if (warp >= 4 && warp < 8) tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), 0x86868686u);   // ue8m0 2^7 everywhere
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t acc0 = tmem_base + T4_SF_COLS;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0, ul = 0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
+                const uint32_t p = u / qblocks, q0 = (u % qblocks) * TC_QROWS;
+                const int32_t qrow = (int32_t)(p * rowstride_q + q0);
+                mbar_wait(bar_afree, (ul & 1) ^ 1);
+                mbar_expect_tx(bar_a, T4_A_BYTES);
+                tma_load_2d(sA, &map_q, 0, qrow, bar_a);
+                tma_load_2d(sA + 128 * T4_ROWBYTES, &map_q, 0, qrow + 128, bar_a);
+                const int32_t trow = (int32_t)(p * rowstride_t);
+                for (uint32_t j = 0; j < ntiles; j++, g++) {
+                    const uint32_t s = g % T4_STAGES, ph = (g / T4_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_expect_tx(bar_full + 8 * s, T4_B_BYTES);
+                    tma_load_2d(sB + s * T4_B_BYTES, &map_t, 0, trow + (int32_t)(j * T4_NCOLS), bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_mxf4(128, T4_NCOLS);
+            const uint32_t sfa = tmem_base, sfb = tmem_base + 16;
+            uint32_t g = 0, ul = 0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
+                mbar_wait(bar_a, ul & 1);
+                tc_fence_after();
+                for (uint32_t j = 0; j < ntiles; j++, g++) {
+                    const uint32_t s = g % T4_STAGES, ph = (g / T4_STAGES) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t bbase = sB + s * T4_B_BYTES;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        mbar_wait(bar_tempty + 8 * h, (g & 1) ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {   // 4 K-steps of 64 e2m1 (32 B) in the 128-byte row
+                            const uint64_t ad = smem_desc_sw128(sA + h * 128 * T4_ROWBYTES + k * 32);
+                            const uint64_t bd = smem_desc_sw128(bbase + k * 32);
+                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, k != 0 ? 1u : 0u);
+                        }
+                        umma_commit(bar_tfull + 8 * h);
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_afree);
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t ew = warp - 4;
+        const uint32_t quad = warp & 3, h = (ew >> 2) & 1, ch = ew >> 3;   // TMEM lane quadrant, accumulator, column part
+        const uint32_t row = h * 128 + quad * 32 + lane;
+        // column parts of the 240-column accumulator: [0, 128) = 4 chunks of 32, [128, 240) = 3 chunks of 32 + one of 16
+        const uint32_t taddr = acc0 + ((quad * 32u) << 16) + h * T4_NCOLS + ch * 128;
+        const uint32_t cw = ch ? T4_NCOLS - 128 : 128;
+        uint32_t raw0[32], raw1[32];
+        uint32_t g = 0;
+        for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + row;
+            float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
+            float tbase = (float)(ch * 128) + TC_KEY_BIAS;
+            for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)T4_NCOLS) {
+                mbar_wait(bar_tfull + 8 * h, g & 1);
+                tc_fence_after();
+                const uint32_t tile0 = j * T4_NCOLS + ch * 128;
+                if ((dbg & 2) || tile0 >= n2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                    continue;
+                }
+                const bool masked = tile0 + cw > n2;
+                const uint32_t nvalid = n2 - tile0;
+                tmem_ld32(taddr, raw0);
+                tmem_wait_ld_regs(raw0);
+                tmem_ld32(taddr + 32, raw1);
+                if (masked) drain_chunk<0, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<0, false>(raw0, nvalid, tbase, r0, r1);
+                tmem_wait_ld_regs(raw1);
+                tmem_ld32(taddr + 64, raw0);
+                if (masked) drain_chunk<32, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<32, false>(raw1, nvalid, tbase, r0, r1);
+                tmem_wait_ld_regs(raw0);
+                if (ch == 0) {
+                    tmem_ld32(taddr + 96, raw1);
+                    if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
+                    tmem_wait_ld_regs(raw1);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                    if (masked) drain_chunk<96, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<96, false>(raw1, nvalid, tbase, r0, r1);
+                } else {
+                    uint32_t raw2[16];
+                    tmem_ld16(taddr + 96, raw2);
+                    if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
+                    tmem_wait_ld_regs16(raw2);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                    if (masked) drain_chunk<96, true, 16>(raw2, nvalid, tbase, r0, r1); else drain_chunk<96, false, 16>(raw2, nvalid, tbase, r0, r1);
+                }
+            }
+            if (q < n1) {
+                uint32_t out[2];
+                const float ks[2] = {r0, r1};
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t ki = __float2uint_rz(ks[i]);
+                    out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                : 0xffffffffu;
+                }
+                part[((size_t)p * TC_COLSPLIT + ch) * n1 + q] = make_uint2(out[0], out[1]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Sixteen lanes per query: merge the column parts into (best group, best other group), evaluate the 16 descriptors
+// of those two 8-column groups with XOR + POPC on the original descriptors, and keep their two smallest
+// (distance, index) keys. out[p][q] = final (best, second).
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
                                                      size_t stride_words, uint32_t n1, uint32_t n2,
                                                      const uint2 *__restrict__ part, uint2 *__restrict__ out) {
-    static_assert(TC_GROUP == 8, "eight lanes per query");
-    const uint32_t sub = threadIdx.x & 7;
-    const uint32_t q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3), p = blockIdx.y;
+    static_assert(TC_GROUP == 8, "two groups of eight lanes per query");
+    const uint32_t sub = threadIdx.x & 15;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4), p = blockIdx.y;
     const bool live = q < n1;
-    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu, key = 0xffffffffu;
+    uint32_t key = 0xffffffffu;
     if (live) {
+        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;   // group keys: (best distance in the group) << 22 | first column
 #pragma unroll
         for (int s = 0; s < TC_COLSPLIT; s++) {
             const uint2 v = part[((size_t)p * TC_COLSPLIT + s) * n1 + q];
@@ -297,9 +501,9 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
             k2 = min(min(k2, v.y), hi);
             k1 = lo;
         }
-        const uint32_t i1 = k1 & KNN_IDX_MASK;
-        const uint32_t col = (i1 & ~7u) + sub;
-        if (col < n2 && col != i1) {
+        const uint32_t gk = (sub < 8) ? k1 : k2;
+        const uint32_t col = (gk & KNN_IDX_MASK) + (sub & 7);
+        if (gk != 0xffffffffu && col < n2) {
             const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
             const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
             const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
@@ -308,9 +512,13 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
             key = (d << KNN_IDX_BITS) | col;
         }
     }
+    uint32_t best = key;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
-    if (live && sub == 0) out[(size_t)p * n1 + q] = make_uint2(k1, min(k2, key));
+    for (int o = 1; o < 16; o <<= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    uint32_t second = (key == best) ? 0xffffffffu : key;   // keys of distinct columns are distinct
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
+    if (live && sub == 0) out[(size_t)p * n1 + q] = make_uint2(best, second);
 }
 
 static int make_map(CUtensorMap *m, const void *base, uint64_t rows) {
@@ -326,47 +534,69 @@ bool hamming_tc_eligible(const HammingPlan &pl) {
 
 // WS_KNN_PART = [P][TC_COLSPLIT][n1] column-part results followed by [P][n1] final keys; *final_part points at
 // the latter, which k_knn2_finish reads as a single split.
+static bool hamming_tc_use_fp4() {
+    if (const char *e = getenv("VB_HAMMING_FP4")) return atoi(e) != 0;
+    return true;
+}
+
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                       const uint2 **final_part) {
+    const bool fp4 = hamming_tc_use_fp4();
     if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         ctx->func_attr_done |= 1u;
     }
     const uint32_t P = pl.P, n1 = pl.n1, n2 = pl.n2;
     const bool seq = P > 1 && n1 == n2 && stride_words == (size_t)n1 * 8 && d2 == d1 + stride_words;
+    const uint32_t rowbytes = fp4 ? T4_ROWBYTES : TC_KBYTES;
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
-    if ((rc = ctx->ws_ensure(WS_EXP, rows_total * TC_KBYTES))) return rc;
+    if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (TC_COLSPLIT + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
+    auto expand = [&](const uint32_t *src, uint32_t rows, uint32_t frames, uint8_t *dst) {
+        if (fp4) {
+            k_expand_e2m1<<<dim3(div_up(rows * 8, 256), frames), 256, 0, ctx->stream>>>(src, stride_words, rows, frames, dst);
+        } else {
+            k_expand_pm1<<<(unsigned)div_up64((size_t)frames * rows * 16, 256), 256, 0, ctx->stream>>>(src, stride_words, rows,
+                                                                                                        frames, dst);
+        }
+        ctx->launches++;
+    };
     ctx->prof_begin("expand");
     if (seq) {
-        Et = E + (size_t)n1 * TC_KBYTES;
-        const size_t thr = (size_t)(P + 1) * n1 * 16;
-        k_expand_pm1<<<(unsigned)div_up64(thr, 256), 256, 0, ctx->stream>>>(d1, stride_words, n1, P + 1, E);
-        ctx->launches++;
+        Et = E + (size_t)n1 * rowbytes;
+        expand(d1, n1, P + 1, E);
     } else {
-        Et = E + (size_t)P * n1 * TC_KBYTES;
-        k_expand_pm1<<<(unsigned)div_up64((size_t)P * n1 * 16, 256), 256, 0, ctx->stream>>>(d1, stride_words, n1, P, Eq);
-        k_expand_pm1<<<(unsigned)div_up64((size_t)P * n2 * 16, 256), 256, 0, ctx->stream>>>(d2, stride_words, n2, P, Et);
-        ctx->launches += 2;
+        Et = E + (size_t)P * n1 * rowbytes;
+        expand(d1, n1, P, Eq);
+        expand(d2, n2, P, Et);
     }
     ctx->prof_end("expand");
     VB_CUDA(cudaGetLastError());
     CUtensorMap mq, mt;
-    if ((rc = make_map(&mq, Eq, (uint64_t)P * n1))) return rc;
-    if ((rc = make_map(&mt, Et, (uint64_t)P * n2))) return rc;
+    if (fp4) {
+        if ((rc = make_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Eq, T4_ROWBYTES, (uint64_t)P * n1, 128, 128))) return rc;
+        if ((rc = make_map_2d(&mt, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Et, T4_ROWBYTES, (uint64_t)P * n2, 128, T4_NCOLS))) return rc;
+    } else {
+        if ((rc = make_map(&mq, Eq, (uint64_t)P * n1))) return rc;
+        if ((rc = make_map(&mt, Et, (uint64_t)P * n2))) return rc;
+    }
     const uint32_t nunits = div_up(n1, TC_QROWS) * P;
     const uint32_t grid = nunits < (uint32_t)ctx->sm_count ? nunits : (uint32_t)ctx->sm_count;   // one persistent CTA per SM
-    ctx->prof_begin("hamming");
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
     uint2 *fixed = part + (size_t)P * TC_COLSPLIT * n1;
     static const int dbg = getenv("VB_TC_DBG") ? atoi(getenv("VB_TC_DBG")) : 0;
-    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    ctx->prof_begin("hamming");
+    if (fp4)
+        k_knn2_tc4<<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else
+        k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
-    k_knn2_tc_fix<<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
+    k_knn2_tc_fix<<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
     ctx->prof_end("knnfix");
     ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
