@@ -291,6 +291,7 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 // of 240 columns (512 = 32 + 2 * 240), so a train tile is 240 descriptors.
 constexpr int T4_NCOLS = 240;                          // train descriptors per tile (UMMA N)
 constexpr int T4_STAGES = 4;                           // B ring depth
+constexpr int T4_PARTS = 4;                            // column parts of an accumulator (one draining warp each per quadrant)
 constexpr int T4_ROWBYTES = 128;                       // expanded descriptor: 256 e2m1 values
 constexpr uint32_t T4_A_BYTES = 2 * 128 * T4_ROWBYTES;        // [half][128 rows][128 B]
 constexpr uint32_t T4_B_BYTES = T4_NCOLS * T4_ROWBYTES;       // [240 rows][128 B] = 30 atoms of 1 KB
@@ -339,7 +340,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4 * TC_COLSPLIT);   // one arrival per draining warp
+            mbar_init(bar_tempty + 8 * s, 4 * T4_PARTS);   // every draining warp reads a part of every accumulator
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
@@ -409,67 +410,72 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             }
         }
     } else if (warp >= 4) {
+        // 16 draining warps = 4 TMEM lane quadrants x 4 column parts; every warp takes its part of BOTH accumulators
+        // (a warp may read any column of its own quadrant), so a part is at most 64 columns: it is loaded into
+        // registers in one go and the accumulator is handed back to the MMA warp before any of it is reduced.
         const uint32_t ew = warp - 4;
-        const uint32_t quad = warp & 3, h = (ew >> 2) & 1, ch = ew >> 3;   // TMEM lane quadrant, accumulator, column part
-        const uint32_t row = h * 128 + quad * 32 + lane;
-        // column parts of the 240-column accumulator: [0, 128) = 4 chunks of 32, [128, 240) = 3 chunks of 32 + one of 16
-        const uint32_t taddr = acc0 + ((quad * 32u) << 16) + h * T4_NCOLS + ch * 128;
-        const uint32_t cw = ch ? T4_NCOLS - 128 : 128;
+        const uint32_t quad = warp & 3, cp = ew >> 2;
+        // parts of the 240 columns: [0,64) [64,128) [128,192) [192,240) — the last one is 32 + 16
+        const uint32_t c0 = cp * 64;
+        const bool wide = cp != 3;
+        const uint32_t cw = wide ? 64 : T4_NCOLS - 192;
         uint32_t raw0[32], raw1[32];
         uint32_t g = 0;
         for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + row;
-            float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
-            float tbase = (float)(ch * 128) + TC_KEY_BIAS;
+            const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
+            float r0[2] = {TC_KEY_NONE, TC_KEY_NONE}, r1[2] = {TC_KEY_NONE, TC_KEY_NONE};   // per row half
+            float tbase = (float)c0 + TC_KEY_BIAS;
             for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)T4_NCOLS) {
-                mbar_wait(bar_tfull + 8 * h, g & 1);
-                tc_fence_after();
-                const uint32_t tile0 = j * T4_NCOLS + ch * 128;
-                if ((dbg & 2) || tile0 >= n2) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-                    continue;
-                }
+                const uint32_t tile0 = j * T4_NCOLS + c0;
+                const bool skip = (dbg & 2) || tile0 >= n2;   // (dbg 2: MMA floor measurement) / nothing valid in this part
                 const bool masked = tile0 + cw > n2;
-                const uint32_t nvalid = n2 - tile0;
-                tmem_ld32(taddr, raw0);
-                tmem_wait_ld_regs(raw0);
-                tmem_ld32(taddr + 32, raw1);
-                if (masked) drain_chunk<0, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<0, false>(raw0, nvalid, tbase, r0, r1);
-                tmem_wait_ld_regs(raw1);
-                tmem_ld32(taddr + 64, raw0);
-                if (masked) drain_chunk<32, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<32, false>(raw1, nvalid, tbase, r0, r1);
-                tmem_wait_ld_regs(raw0);
-                if (ch == 0) {
-                    tmem_ld32(taddr + 96, raw1);
-                    if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
-                    tmem_wait_ld_regs(raw1);
+                const uint32_t nvalid = skip ? 0 : n2 - tile0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t taddr = acc0 + ((quad * 32u) << 16) + h * T4_NCOLS + c0;
+                    mbar_wait(bar_tfull + 8 * h, g & 1);
+                    tc_fence_after();
+                    if (!skip) {
+                        tmem_ld32(taddr, raw0);
+                        if (wide) {
+                            tmem_ld32(taddr + 32, raw1);
+                            tmem_wait_ld_regs(raw0);
+                            tmem_wait_ld_regs(raw1);
+                        } else {
+                            tmem_ld16(taddr + 32, *reinterpret_cast<uint32_t(*)[16]>(raw1));
+                            tmem_wait_ld_regs(raw0);
+                            tmem_wait_ld_regs16(*reinterpret_cast<uint32_t(*)[16]>(raw1));
+                        }
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-                    if (masked) drain_chunk<96, true>(raw1, nvalid, tbase, r0, r1); else drain_chunk<96, false>(raw1, nvalid, tbase, r0, r1);
-                } else {
-                    uint32_t raw2[16];
-                    tmem_ld16(taddr + 96, raw2);
-                    if (masked) drain_chunk<64, true>(raw0, nvalid, tbase, r0, r1); else drain_chunk<64, false>(raw0, nvalid, tbase, r0, r1);
-                    tmem_wait_ld_regs16(raw2);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
-                    if (masked) drain_chunk<96, true, 16>(raw2, nvalid, tbase, r0, r1); else drain_chunk<96, false, 16>(raw2, nvalid, tbase, r0, r1);
+                    if (skip) continue;
+                    if (masked) {
+                        drain_chunk<0, true>(raw0, nvalid, tbase, r0[h], r1[h]);
+                        if (wide) drain_chunk<32, true>(raw1, nvalid, tbase, r0[h], r1[h]);
+                        else drain_chunk<32, true, 16>(*reinterpret_cast<uint32_t(*)[16]>(raw1), nvalid, tbase, r0[h], r1[h]);
+                    } else {
+                        drain_chunk<0, false>(raw0, nvalid, tbase, r0[h], r1[h]);
+                        if (wide) drain_chunk<32, false>(raw1, nvalid, tbase, r0[h], r1[h]);
+                        else drain_chunk<32, false, 16>(*reinterpret_cast<uint32_t(*)[16]>(raw1), nvalid, tbase, r0[h], r1[h]);
+                    }
                 }
             }
-            if (q < n1) {
-                uint32_t out[2];
-                const float ks[2] = {r0, r1};
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const uint32_t ki = __float2uint_rz(ks[i]);
-                    out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
-                                                : 0xffffffffu;
+            for (int h = 0; h < 2; h++) {
+                const uint32_t q = qb + h * 128;
+                if (q < n1) {
+                    uint32_t out[2];
+                    const float ks[2] = {r0[h], r1[h]};
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint32_t ki = __float2uint_rz(ks[i]);
+                        out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                    : 0xffffffffu;
+                    }
+                    part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(out[0], out[1]);
                 }
-                part[((size_t)p * TC_COLSPLIT + ch) * n1 + q] = make_uint2(out[0], out[1]);
             }
         }
     }
@@ -485,7 +491,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 // of those two 8-column groups with XOR + POPC on the original descriptors, and keep their two smallest
 // (distance, index) keys. out[p][q] = final (best, second).
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
-                                                     size_t stride_words, uint32_t n1, uint32_t n2,
+                                                     size_t stride_words, uint32_t n1, uint32_t n2, uint32_t nparts,
                                                      const uint2 *__restrict__ part, uint2 *__restrict__ out) {
     static_assert(TC_GROUP == 8, "two groups of eight lanes per query");
     const uint32_t sub = threadIdx.x & 15;
@@ -494,9 +500,8 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
     uint32_t key = 0xffffffffu;
     if (live) {
         uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;   // group keys: (best distance in the group) << 22 | first column
-#pragma unroll
-        for (int s = 0; s < TC_COLSPLIT; s++) {
-            const uint2 v = part[((size_t)p * TC_COLSPLIT + s) * n1 + q];
+        for (uint32_t s = 0; s < nparts; s++) {
+            const uint2 v = part[((size_t)p * nparts + s) * n1 + q];
             const uint32_t lo = min(k1, v.x), hi = max(k1, v.x);   // v.x < v.y and k1 < k2
             k2 = min(min(k2, v.y), hi);
             k1 = lo;
@@ -553,7 +558,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (TC_COLSPLIT + 1) * n1 * sizeof(uint2)))) return rc;
+    const uint32_t nparts = fp4 ? T4_PARTS : TC_COLSPLIT;
+    if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
     auto expand = [&](const uint32_t *src, uint32_t rows, uint32_t frames, uint8_t *dst) {
@@ -587,7 +593,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     const uint32_t nunits = div_up(n1, TC_QROWS) * P;
     const uint32_t grid = nunits < (uint32_t)ctx->sm_count ? nunits : (uint32_t)ctx->sm_count;   // one persistent CTA per SM
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
-    uint2 *fixed = part + (size_t)P * TC_COLSPLIT * n1;
+    uint2 *fixed = part + (size_t)P * nparts * n1;
     static const int dbg = getenv("VB_TC_DBG") ? atoi(getenv("VB_TC_DBG")) : 0;
     ctx->prof_begin("hamming");
     if (fp4)
@@ -596,7 +602,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
-    k_knn2_tc_fix<<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, part, fixed);
+    k_knn2_tc_fix<<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     ctx->prof_end("knnfix");
     ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
