@@ -91,13 +91,18 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     if ((rc = ctx->ws_ensure(WS_RESULT, (size_t)P * sizeof(vb_pair_result)))) return rc;
     if (out_matches && (rc = ctx->ws_ensure(WS_OUTMATCH, (size_t)P * k * 8))) return rc;
     // Software pipeline over sub-batches: the upload of batch b+1 and the download of batch b-1 run on two
-    // copy streams while batch b computes (they only overlap when the caller's buffers are pinned). The first
-    // batch is small because its upload is the one nothing hides.
+    // copy streams while batch b computes (they only overlap when the caller's buffers are pinned).
     std::vector<uint32_t> cut;   // cut[b] .. cut[b+1] = pairs of sub-batch b
     cut.push_back(0);
     if (P >= 512) {
-        cut.push_back(64);
-        while (P - cut.back() > 320) cut.push_back(cut.back() + 256);
+        // doubling sizes: each upload is hidden by the (about equally long) compute of the batch before it; the first
+        // batch is tiny because nothing hides its upload, the last one moderate because nothing hides its download
+        uint32_t sz = 32;
+        while (P - cut.back() > sz + 192) {
+            cut.push_back(cut.back() + sz);
+            if (sz < 384) sz *= 2;
+        }
+        if (P - cut.back() > 256) cut.push_back(P - 192);
     }
     cut.push_back(P);
     const uint32_t nb = (uint32_t)cut.size() - 1;
