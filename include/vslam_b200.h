@@ -137,6 +137,14 @@ int vb_ransac_score(vb_ctx *ctx, const float *corr, uint32_t m, const float *F, 
                     int32_t *n_inliers, float *score);
 int vb_ransac_score_d(vb_ctx *ctx, const float *corr_d, uint32_t m, const float *F_d, uint32_t h, float threshold,
                       int32_t *n_inliers_d, float *score_d);
+/* Inlier counts only (the first member of compute_fundamental_residual's return pair, :138) — the kernel the pair pipeline
+ * uses: a and s = x2 . a follow the reference's rounding sequence, the rest of the residual is evaluated with FMAs and an
+ * approximate reciprocal under a rigorous error bound, and any evaluation within that bound of the threshold is redone
+ * with the reference's sequence, so the counts equal vb_ransac_score's exactly. */
+int vb_ransac_counts(vb_ctx *ctx, const float *corr, uint32_t m, const float *F, uint32_t h, float threshold,
+                     int32_t *n_inliers);
+int vb_ransac_counts_d(vb_ctx *ctx, const float *corr_d, uint32_t m, const float *F_d, uint32_t h, float threshold,
+                       int32_t *n_inliers_d);
 /* The 8-point solve alone (compute_fundamental, :69-103) for h minimal samples: p1set/p2set [h][8][2]. */
 int vb_ransac_solve8(vb_ctx *ctx, const float *p1set, const float *p2set, uint32_t h, float *F);
 

@@ -451,3 +451,84 @@ def test_knn2_l2f_tensor_path_equals_exact_kernel_at_size(ctx, oracle, monkeypat
     assert np.array_equal(it, ie) and np.array_equal(bits(dt), bits(de))
     oi, od = oracle.knn2_l2f(np.ascontiguousarray(d1[:200]), d2)
     assert np.array_equal(it[:200], oi) and np.array_equal(bits(dt[:200]), bits(od))
+
+
+# ---------------------------------------------------------------- counting kernel (the pair pipeline's scorer)
+@pytest.mark.parametrize("m,H,thr", [(1, 3, 10.0), (129, 70, 10.0), (3500, 1024, 10.0), (3500, 300, 0.2), (20000, 257, 10.0),
+                                     (8193, 64, 1e-6), (3000, 64, 1e6)])
+def test_counts_equal_exact_scoring(ctx, oracle, m, H, thr):
+    """k_count (relaxed arithmetic + error bound + exact fallback) returns the reference's counts for every hypothesis."""
+    corr = synth.correspondences(max(m, 8), m + H)[:m].copy()
+    Fs = _hyp_bank(oracle, synth.correspondences(512, 3), H, m)
+    cnt = ctx.ransac_counts(corr, Fs, thr)
+    ecnt, _ = ctx.ransac_score(corr, Fs, thr)
+    assert np.array_equal(cnt, ecnt)
+    pick = np.r_[0:min(H, 6)]
+    ocnt, _ = _oracle_scores(oracle, corr, Fs[pick], thr)
+    assert np.array_equal(cnt[pick], ocnt)
+
+
+def test_counts_threshold_exactly_on_residuals(ctx, oracle):
+    """Adversarial thresholds: thr set to residual values that actually occur (e == thr must count, the next float below
+    must not), so the decision can only come out right through the exact fallback."""
+    corr = synth.correspondences(2000, 21)
+    Fs = _hyp_bank(oracle, corr, 40, 5)
+    p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+    mm = np.stack([np.arange(len(corr)), np.arange(len(corr))], 1).astype(np.int32)
+    rng = np.random.default_rng(2)
+    for h in (0, 7, 19, 33):
+        _, e, _, _ = oracle.residual(p1, p2, mm, Fs[h].reshape(3, 3), 10.0)
+        finite = e[np.isfinite(e) & (e > 0)]
+        for thr in rng.choice(finite, 6, replace=False):
+            for t in (np.float32(thr), np.nextafter(np.float32(thr), np.float32(0)), np.nextafter(np.float32(thr), np.float32(np.inf))):
+                cnt = ctx.ransac_counts(corr, Fs, float(t))
+                ecnt, _ = ctx.ransac_score(corr, Fs, float(t))
+                assert np.array_equal(cnt, ecnt)
+                assert cnt[h] == int((e <= t).sum())
+
+
+def test_counts_degenerate_models_and_coordinates(ctx, oracle, golden):
+    """Zero / NaN / inf / huge F entries and the golden set's x/0, 0/0 cases: everything uncertain goes to the exact path."""
+    g = golden
+    p1, p2, mm = g["res_p1"], g["res_p2"], g["res_matches"]
+    corr = np.ascontiguousarray(np.concatenate([p1[mm[:, 0]], p2[mm[:, 1]]], 1), np.float32)
+    Fs = g["res_F"].reshape(-1, 9).astype(np.float32)
+    cnt = ctx.ransac_counts(corr, Fs, float(g["res_thr"]))
+    assert np.array_equal(cnt, g["res_cnt"])
+    corr2 = synth.correspondences(1500, 4)
+    bank = _hyp_bank(oracle, corr2, 16, 1)
+    weird = np.zeros((8, 9), np.float32)
+    weird[1] = np.nan
+    weird[2] = [0, 0, 0, 0, 0, 0, 0, 0, 1]            # a0 == 0 everywhere: x/0
+    weird[3] = bank[0] * np.float32(1e30)
+    weird[4] = bank[1] * np.float32(1e-30)
+    weird[5] = [0, 0, 1e-38, 0, 0, 0, 0, 0, 1]        # a0^2 underflows
+    weird[6] = np.inf
+    weird[7] = bank[2]
+    Fs2 = np.concatenate([bank, weird])
+    for thr in (10.0, 0.0, np.inf):
+        cnt = ctx.ransac_counts(corr2, Fs2, thr)
+        ecnt, _ = ctx.ransac_score(corr2, Fs2, thr)
+        assert np.array_equal(cnt, ecnt)
+    big = corr2.copy()
+    big[::7] *= np.float32(1e18)                      # squares overflow
+    cnt = ctx.ransac_counts(big, Fs2, 10.0)
+    ecnt, _ = ctx.ransac_score(big, Fs2, 10.0)
+    assert np.array_equal(cnt, ecnt)
+
+
+def test_pipeline_lazy_scores_equal_full_scoring(ctx, oracle, monkeypatch):
+    """vb_pairs_run with the counting kernel + tie scoring == the same call forced through full scoring, on data with many
+    ties at the largest count (noise-free correspondences)."""
+    pts, desc = synth.sequence(9, 1500, 3, noise_px=0.0, outlier_frac=0.2)
+    prm = ctx.params(0.7, 8, 256, 10.0, 5)
+    res_lazy, m_lazy = ctx.pairs_run(pts, desc, prm)
+    monkeypatch.setenv("VB_RANSAC_LAZY", "0")
+    res_full, m_full = ctx.pairs_run(pts, desc, prm)
+    for k in ("status", "n_tentative", "n_matches", "best_hyp", "n_inliers"):
+        assert np.array_equal(res_lazy[k], res_full[k]), k
+    assert np.array_equal(bits(res_lazy["score"]), bits(res_full["score"]))
+    assert np.array_equal(bits(res_lazy["F"]), bits(res_full["F"]))
+    for i, n in enumerate(res_lazy["n_matches"]):
+        assert np.array_equal(m_lazy[i, :n], m_full[i, :n])
+    assert (res_lazy["n_matches"] > 100).all()

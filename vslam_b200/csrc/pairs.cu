@@ -39,7 +39,7 @@ static int pairs_core(vb_ctx *ctx, uint32_t P, const float2 *p1_base, const floa
     if ((rc = ransac_plan(ctx, P, n1, n1, prm.max_iterations, prm.min_items, &rp))) return rc;
     ProblemDims dims{ctx->ws[WS_M].as<uint32_t>(), 0, seed0};
     return ransac_run(ctx, rp, ctx->ws[WS_CORR].as<float4>(), dims, prm.threshold, results_d, nullptr,
-                      ctx->ws[WS_TENT].as<int2>(), out_matches_d);
+                      ctx->ws[WS_TENT].as<int2>(), out_matches_d, true);
 }
 
 static int check_params(const vb_pair_params *p, uint32_t bytes, uint32_t n2) {

@@ -52,12 +52,16 @@ struct RansacSelectArgs {
     int2 *out_matches;      // [P][mcap] or nullptr
     int score_only;
     int prefolded;          // cnt/score already hold the folded totals (k_fold ran first)
+    int lazy;               // counts came from k_count: no residual sums; k_select scores the tied hypotheses itself
+    uint32_t *tied;         // [P][H] scratch list of tied hypotheses (lazy mode)
 };
 
 int ransac_plan(vb_ctx *ctx, uint32_t P, uint32_t mcap, uint32_t m_upper, uint32_t H, int min_items, RansacPlan *pl);
 int ransac_launch_score(vb_ctx *ctx, const RansacPlan &pl, const float4 *corr, ProblemDims dims, const float *F_all,
                         float thr);
+// lazy = true: count with k_count (approximate residual + exact fallback) and compute residual sums only for the
+// hypotheses that tie at the largest count; per-hypothesis scores of the others are then not available (0).
 int ransac_run(vb_ctx *ctx, const RansacPlan &pl, const float4 *corr, ProblemDims dims, float thr,
-               vb_pair_result *results_d, uint8_t *mask_d, const int2 *tent_d, int2 *out_matches_d);
+               vb_pair_result *results_d, uint8_t *mask_d, const int2 *tent_d, int2 *out_matches_d, bool lazy);
 
 }  // namespace vb
