@@ -286,13 +286,15 @@ def main():
     evals = float(args.hyps) * float(sum_tent)                    # (hypothesis, match) evaluations per launch
     logical_bytes = 16.0 * evals + 36.0 * args.hyps * P + 8.0 * args.hyps * P
     achieved = logical_bytes / (score_ms_avg * 1e-3) / 1e9
-    roofline = {"kernel": "k_score (RANSAC residual / inlier scoring)", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "k_count (RANSAC residual / inlier scoring of every hypothesis over every match)", "bound": "hbm",
+                "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("k_score", P, k, args.hyps),
+                "traffic": ncu_traffic("k_count", P, k, args.hyps),
                 "peak_source": peak_src, "evals_per_launch": evals, "ms_per_launch": score_ms_avg,
                 "hypotheses_scored_per_s": args.hyps * P / (score_ms_avg * 1e-3),
                 "note": "logical bytes = 16 B x hypotheses x matches (SURVEY 8d); tiles are L2/smem resident so DRAM "
-                        "traffic is far lower and the kernel is FP32/FP64-issue bound (DESIGN.md)"}
+                        "traffic is far lower and the kernel is FP32-issue bound (DESIGN.md); residual sums are computed "
+                        "afterwards only for the hypotheses tied at the largest count (k_select)"}
     step_ms = ms_total / args.steps
     shares = {n: (v / step_ms if v and v > 0 else None) for n, v in kt.items()}
 

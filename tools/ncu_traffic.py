@@ -11,7 +11,7 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 res = {}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    key = "k_score" if "k_score" in name else "k_knn2_tc4" if "k_knn2_tc4" in name else None
+    key = "k_count" if "k_count" in name else "k_score" if "k_score" in name else "k_knn2_tc4" if "k_knn2_tc4" in name else None
     if not key or key in res:
         continue
     tot = 0.0
