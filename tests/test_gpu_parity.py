@@ -419,6 +419,10 @@ def _float_descriptors(kind, n1, n2, dim, seed):
         d1[:m] = d2[:m] + 0.05 * rng.standard_normal((m, dim)).astype(np.float32)
     elif kind == "sift":          # integer-valued, large norms: many exactly equal distances
         d1, d2 = np.abs(d1 * 40).round().astype(np.float32), np.abs(d2 * 40).round().astype(np.float32)
+    elif kind == "near":          # train rows = a few prototypes + perturbations far below bf16 resolution: the GEMM cannot order them
+        proto = rng.standard_normal((7, dim)).astype(np.float32)
+        d2 = proto[rng.integers(0, 7, n2)] + (1e-5 * rng.standard_normal((n2, dim))).astype(np.float32)
+        d1 = proto[rng.integers(0, 7, n1)] + (1e-5 * rng.standard_normal((n1, dim))).astype(np.float32)
     elif kind == "equal":         # every train row equal but one: every chunk minimum ties, exact scan fallback
         d2[:] = d2[0]
         d2[min(7, n2 - 1)] += 1e-3
@@ -430,7 +434,8 @@ def _float_descriptors(kind, n1, n2, dim, seed):
 
 @pytest.mark.parametrize("kind,n1,n2,dim", [("unit", 256, 256, 128), ("unit", 300, 700, 64), ("gauss", 1000, 513, 128),
                                             ("sift", 1500, 2100, 128), ("unit", 37, 2, 128), ("equal", 500, 40, 64),
-                                            ("equal", 300, 1000, 128), ("sift", 700, 300, 64)])
+                                            ("equal", 300, 1000, 128), ("sift", 700, 300, 64), ("near", 600, 900, 128),
+                                            ("near", 257, 300, 64)])
 def test_knn2_l2f_tensor_path_bit_exact(ctx, oracle, monkeypatch, kind, n1, n2, dim):
     """The tcgen05 (bf16 GEMM + exact re-evaluation) path returns the oracle's indices and distance bits."""
     monkeypatch.setenv("VB_L2_TC", "1")

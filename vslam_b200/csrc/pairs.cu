@@ -105,6 +105,16 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
         if (P - cut.back() > 256) cut.push_back(P - 192);
     }
     cut.push_back(P);
+    if (const char *e = getenv("VB_PAIRS_SCHEDULE")) {   // measurement override: comma-separated sub-batch sizes
+        cut.assign(1, 0u);
+        for (const char *q = e; *q && cut.back() < P;) {
+            const uint32_t sz = (uint32_t)strtoul(q, const_cast<char **>(&q), 10);
+            if (sz == 0) break;
+            cut.push_back(cut.back() + sz < P ? cut.back() + sz : P);
+            if (*q == ',') q++;
+        }
+        if (cut.back() < P) cut.push_back(P);
+    }
     const uint32_t nb = (uint32_t)cut.size() - 1;
     if (!ctx->copy_in) {
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
