@@ -411,6 +411,21 @@ def kdtree_stage(ctx, torch, dev, pts, k):
                 ms[name].append(ctx.profile_ms(name))
     ctx.profile(False)
     L.vb_kdtree_free(tree)
+    # batched build: one tree per frame of a 256-frame block in one launch (one CTA per tree)
+    nb = min(256, len(pts))
+    blk_d = torch.from_numpy(np.ascontiguousarray(pts[:nb])).to(dev)
+    handles = (C.c_void_p * nb)()
+    bms = []
+    for it in range(5):
+        ctx.profile(it >= 2)
+        ctx._chk(L.vb_kdtree_build_batch_d(ctx.h, blk_d.data_ptr(), nb, k, handles))
+        torch.cuda.synchronize(dev)
+        if it >= 2:
+            bms.append(ctx.profile_ms("kd_build"))
+        L.vb_kdtree_free_batch(handles, nb)
+    ctx.profile(False)
+    res["gpu_batched_build"] = {"trees": nb, "ms": float(np.mean(bms)), "trees_per_s": nb / (float(np.mean(bms)) * 1e-3),
+                                "us_per_tree": float(np.mean(bms)) * 1e3 / nb}
     res["gpu_ms"] = {n: float(np.mean(v)) for n, v in ms.items()}
     res["gpu_queries_per_s"] = {"nearest": k / (res["gpu_ms"]["kd_nearest"] * 1e-3), "radius2": k / (res["gpu_ms"]["kd_radius"] * 1e-3)}
     res["radius2_hits"] = int(tot.value)

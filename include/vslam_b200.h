@@ -63,6 +63,11 @@ uint64_t vb_launch_count(const vb_ctx *ctx);
  * ---------------------------------------------------------------------------------------------- */
 int vb_kdtree_build(vb_ctx *ctx, const float *pts_xy, uint32_t n, vb_tree **out);
 int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_xy_d, uint32_t n, vb_tree **out);
+/* One tree per frame of a sequence in a single launch (one CTA per tree): pts_xy_d [ntrees][n][2] on the device, out[ntrees].
+ * The trees share one allocation; release them together with vb_kdtree_free_batch. (construct_kdtree once per frame,
+ * src/Frame.cpp:76, for every frame of a batch.) */
+int vb_kdtree_build_batch_d(vb_ctx *ctx, const float *pts_xy_d, uint32_t ntrees, uint32_t n, vb_tree **out);
+int vb_kdtree_free_batch(vb_tree **trees, uint32_t ntrees);
 /* Re-create the device tree from a pre-order node array that already exists on the host (what the
  * reference's KDTree::root / frame_kdtree::root hold): pts_preorder[n*2], idx_preorder[n] (NULL = slot
  * numbers). Used by the C++ adapter when a caller hands it a tree it has no device copy of. */

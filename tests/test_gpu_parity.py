@@ -537,3 +537,30 @@ def test_pipeline_lazy_scores_equal_full_scoring(ctx, oracle, monkeypatch):
     for i, n in enumerate(res_lazy["n_matches"]):
         assert np.array_equal(m_lazy[i, :n], m_full[i, :n])
     assert (res_lazy["n_matches"] > 100).all()
+
+
+def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
+    """vb_kdtree_build_batch_d: one tree per frame in one launch == the per-frame builds == the oracle (layout, radius order)."""
+    import torch
+    from vslam_b200.lib import KDTreeHandle
+    nt, n = 6, 3000
+    pts, _ = synth.sequence(nt, n, 12)
+    pts_d = torch.from_numpy(pts).cuda()
+    handles = (C.c_void_p * nt)()
+    ctx._chk(ctx.L.vb_kdtree_build_batch_d(ctx.h, C.c_void_p(pts_d.data_ptr()), nt, n, handles))
+    try:
+        for i in range(nt):
+            view = KDTreeHandle(ctx, None, n)      # non-owning wrapper around the batch's handle
+            view.h = C.c_void_p(handles[i])
+            idx, pp = view.export()
+            assert np.array_equal(idx.astype(np.int32), oracle.kdtree_build(pts[i]))
+            assert view.height == int(np.floor(np.log2(n))) + 1
+            q = np.ascontiguousarray(pts[i][:50] + 0.3, np.float32)
+            off, hits = view.radius(q, 3.0)
+            pre = oracle.kdtree_build(pts[i])
+            for j in range(50):
+                oi, _ = oracle.kdtree_radius(pts[i], pre, q[j], 3.0)
+                assert np.array_equal(hits[off[j]:off[j + 1]].astype(np.int32), oi)
+            view.h = None                          # released with the batch below
+    finally:
+        ctx.L.vb_kdtree_free_batch(handles, nt)

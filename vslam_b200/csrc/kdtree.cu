@@ -484,6 +484,41 @@ int vb_kdtree_build_d(vb_ctx *ctx, const float *pts_d, uint32_t n, vb_tree **out
     return VB_OK;
 }
 
+int vb_kdtree_build_batch_d(vb_ctx *ctx, const float *pts_d, uint32_t ntrees, uint32_t n, vb_tree **out) {
+    VB_REQUIRE(ctx && out && (pts_d || n == 0 || ntrees == 0), VB_ERR_INVALID, "NULL argument");
+    VB_REQUIRE(n < (1u << 30), VB_ERR_INVALID, "too many points");
+    if (ntrees == 0) return VB_OK;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    // one allocation backs every tree ([tree][x | y | idx]); tree 0 owns it, the others are views
+    vb_tree *first = nullptr;
+    int rc = tree_alloc(ctx, n * ntrees, &first);
+    if (rc) return rc;
+    float *base = reinterpret_cast<float *>(first->block);
+    rc = kd_build_launch(ctx, reinterpret_cast<const float2 *>(pts_d), n, ntrees, n, base, base + n,
+                         reinterpret_cast<uint32_t *>(base + 2 * (size_t)n), 3 * (size_t)n);
+    if (rc) { vb_kdtree_free(first); return rc; }
+    uint32_t height = 0;
+    for (uint32_t v = n; v; v >>= 1) height++;
+    for (uint32_t i = 0; i < ntrees; i++) {
+        vb_tree *t = i ? new vb_tree() : first;
+        t->ctx = ctx;
+        t->n = n;
+        t->height = height;
+        t->x = base + (size_t)i * 3 * n;
+        t->y = t->x + n;
+        t->idx = reinterpret_cast<uint32_t *>(t->y + n);
+        if (i) t->block = nullptr;
+        out[i] = t;
+    }
+    return VB_OK;
+}
+
+int vb_kdtree_free_batch(vb_tree **trees, uint32_t ntrees) {
+    if (!trees) return VB_OK;
+    for (uint32_t i = ntrees; i-- > 0;) vb_kdtree_free(trees[i]);   // views first, the owner (tree 0) last
+    return VB_OK;
+}
+
 int vb_kdtree_build(vb_ctx *ctx, const float *pts, uint32_t n, vb_tree **out) {
     VB_REQUIRE(ctx && out && (pts || n == 0), VB_ERR_INVALID, "NULL argument");
     VB_CUDA(cudaSetDevice(ctx->device));

@@ -39,7 +39,7 @@ assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 60
 
 EXPORTS = [
     "vb_version", "vb_last_error", "vb_create", "vb_destroy", "vb_set_stream", "vb_synchronize", "vb_launch_count",
-    "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
+    "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_build_batch_d", "vb_kdtree_free_batch", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
@@ -73,6 +73,8 @@ def load_library() -> C.CDLL:
     L.vb_launch_count.argtypes = [vp]
     L.vb_kdtree_build.argtypes = [vp, vp, u32, C.POINTER(vp)]
     L.vb_kdtree_build_d.argtypes = [vp, vp, u32, C.POINTER(vp)]
+    L.vb_kdtree_build_batch_d.argtypes = [vp, vp, u32, u32, C.POINTER(vp)]
+    L.vb_kdtree_free_batch.argtypes = [C.POINTER(vp), u32]
     L.vb_kdtree_import.argtypes = [vp, vp, vp, u32, C.POINTER(vp)]
     L.vb_kdtree_free.argtypes = [vp]
     L.vb_kdtree_size.restype = u32
