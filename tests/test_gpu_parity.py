@@ -564,3 +564,39 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
             view.h = None                          # released with the batch below
     finally:
         ctx.L.vb_kdtree_free_batch(handles, nt)
+
+
+def test_scalar_fallback_kernels_in_subprocess():
+    """k_count<2> / k_score<2> (the scalar-instruction versions kept behind VB_COUNT_PACKED=0 / VB_SCORE_PACKED=0, read once per
+    process) and the fp8 matcher (VB_HAMMING_FP4=0) still agree with the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r"""
+import sys, numpy as np
+sys.path[:0] = [%r, %r]
+from oracle_lib import Oracle
+from vslam_b200 import synth
+from vslam_b200.lib import Context
+ctx, orc = Context(0), Oracle()
+corr = synth.correspondences(3000, 5)
+rng = np.random.default_rng(1)
+Fs = np.stack([orc.compute_fundamental(corr[s, :2], corr[s, 2:]).reshape(-1) for s in (rng.choice(3000, 8, replace=False) for _ in range(300))])
+cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+cnt2 = ctx.ransac_counts(corr, Fs, 10.0)
+p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+mm = np.stack([np.arange(3000), np.arange(3000)], 1).astype(np.int32)
+for h in range(0, 300, 37):
+    _, _, n, s = orc.residual(p1, p2, mm, Fs[h].reshape(3, 3), 10.0)
+    assert cnt[h] == n == cnt2[h] and np.float32(s).view(np.uint32) == sc[h:h + 1].view(np.uint32)[0]
+assert np.array_equal(cnt, cnt2)
+fp = synth.frame_pair(2500, 3)
+g = ctx.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], ctx.params(0.7, 8, 256, 10.0, 9))
+o = orc.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], 0.7, 8, 256, 10.0, 9)
+assert g["n"] == o["n"] and np.array_equal(g["matches"], o["matches"]) and np.array_equal(g["F"].view(np.uint32), o["F"].view(np.uint32))
+print("fallback kernels ok")
+""" % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, VB_COUNT_PACKED="0", VB_SCORE_PACKED="0", VB_HAMMING_FP4="0")
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fallback kernels ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
