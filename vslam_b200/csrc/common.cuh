@@ -106,6 +106,7 @@ struct vb_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of vb_pairs_run
+    vb_ctx *twin = nullptr;   // second stream + second set of workspaces: vb_pairs_run alternates sub-batches between the two
     std::vector<cudaEvent_t> events;                      // untimed events for the copy/compute pipeline
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];

@@ -55,6 +55,10 @@ int vb_create(int device, vb_ctx **out) {
 
 int vb_destroy(vb_ctx *c) {
     if (!c) return VB_OK;
+    if (c->twin) {
+        vb_destroy(c->twin);
+        c->twin = nullptr;
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &b : c->ws) b.release();

@@ -120,6 +120,21 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     }
+    // Odd sub-batches run on a twin context (its own stream and workspaces) so that the tail of one sub-batch's kernels
+    // overlaps the head of the next one's: sub-batches are too small to fill the machine through every kernel.
+    static const bool use_twin = !(getenv("VB_PAIRS_TWIN") && atoi(getenv("VB_PAIRS_TWIN")) == 0);
+    if (use_twin && nb > 1 && !ctx->twin) {
+        vb_ctx *t = new vb_ctx();
+        t->device = ctx->device;
+        t->sm_count = ctx->sm_count;
+        if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete t;
+            set_error("cudaStreamCreate failed for the twin context");
+            return VB_ERR_CUDA;
+        }
+        t->stream = t->own_stream;
+        ctx->twin = t;
+    }
     while (ctx->events.size() < 2 * (size_t)nb + 1) {
         cudaEvent_t e;
         VB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -147,12 +162,13 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     const uint32_t *desc32 = reinterpret_cast<const uint32_t *>(desc_d);
     for (uint32_t b = 0; b < nb; b++) {
         const uint32_t p0 = cut[b], pb = cut[b + 1] - cut[b];
-        VB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[b], 0));
-        rc = pairs_core(ctx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
+        vb_ctx *cx = (use_twin && ctx->twin && (b & 1)) ? ctx->twin : ctx;
+        VB_CUDA(cudaStreamWaitEvent(cx->stream, ctx->events[b], 0));
+        rc = pairs_core(cx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
                         desc32 + (size_t)(p0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + p0,
                         res_d + p0, outm_d ? outm_d + (size_t)p0 * k : nullptr);
         if (rc) return rc;
-        VB_CUDA(cudaEventRecord(ctx->events[nb + b], ctx->stream));
+        VB_CUDA(cudaEventRecord(ctx->events[nb + b], cx->stream));
         VB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->events[nb + b], 0));
         VB_CUDA(cudaMemcpyAsync(results + p0, res_d + p0, (size_t)pb * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
                                 ctx->copy_out));
@@ -162,6 +178,11 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     }
     VB_CUDA(cudaStreamSynchronize(ctx->copy_out));
     VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->twin) {
+        VB_CUDA(cudaStreamSynchronize(ctx->twin->stream));
+        ctx->launches += ctx->twin->launches;
+        ctx->twin->launches = 0;
+    }
     return VB_OK;
 }
 
