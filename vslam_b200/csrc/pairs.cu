@@ -67,12 +67,49 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     const uint32_t P = nframes - 1, W = bytes / 4;
     const float2 *pts = reinterpret_cast<const float2 *>(pts_d);
     const uint32_t *desc = reinterpret_cast<const uint32_t *>(desc_d);
-    for (uint32_t b0 = 0; b0 < P; b0 += PAIRS_MAX_BATCH) {
-        const uint32_t pb = (P - b0 < PAIRS_MAX_BATCH) ? P - b0 : PAIRS_MAX_BATCH;
-        rc = pairs_core(ctx, pb, pts + (size_t)b0 * k, pts + (size_t)(b0 + 1) * k, k, desc + (size_t)b0 * k * W,
+    // Batches alternate between the context and its twin (own stream + workspaces) so that the tail of one batch's kernels
+    // overlaps the head of the next one's; the twin starts after everything already queued on the caller's stream and
+    // the caller's stream ends by waiting for the twin.
+    static const bool use_twin = !(getenv("VB_PAIRS_TWIN") && atoi(getenv("VB_PAIRS_TWIN")) == 0);
+    // (not while the profiling brackets are on: they time the context's own stream, one whole batch at a time)
+    const bool split = use_twin && !ctx->profile && P >= 512;
+    const uint32_t batch = split ? (P < 2 * PAIRS_MAX_BATCH ? (P + 1) / 2 : PAIRS_MAX_BATCH) : PAIRS_MAX_BATCH;
+    const bool twin = split && P > batch;
+    if (twin) {
+        if (!ctx->twin) {
+            vb_ctx *t = new vb_ctx();
+            t->device = ctx->device;
+            t->sm_count = ctx->sm_count;
+            if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                delete t;
+                set_error("cudaStreamCreate failed for the twin context");
+                return VB_ERR_CUDA;
+            }
+            t->stream = t->own_stream;
+            ctx->twin = t;
+        }
+        while (ctx->events.size() < 2) {
+            cudaEvent_t e;
+            VB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->events.push_back(e);
+        }
+        VB_CUDA(cudaEventRecord(ctx->events[0], ctx->stream));
+        VB_CUDA(cudaStreamWaitEvent(ctx->twin->stream, ctx->events[0], 0));
+    }
+    uint32_t nb = 0;
+    for (uint32_t b0 = 0; b0 < P; b0 += batch, nb++) {
+        const uint32_t pb = (P - b0 < batch) ? P - b0 : batch;
+        vb_ctx *cx = (twin && (nb & 1)) ? ctx->twin : ctx;
+        rc = pairs_core(cx, pb, pts + (size_t)b0 * k, pts + (size_t)(b0 + 1) * k, k, desc + (size_t)b0 * k * W,
                         desc + (size_t)(b0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + b0,
                         results_d + b0, out_matches_d ? reinterpret_cast<int2 *>(out_matches_d) + (size_t)b0 * k : nullptr);
         if (rc) return rc;
+    }
+    if (twin) {
+        VB_CUDA(cudaEventRecord(ctx->events[1], ctx->twin->stream));
+        VB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[1], 0));
+        ctx->launches += ctx->twin->launches;
+        ctx->twin->launches = 0;
     }
     return VB_OK;
 }
