@@ -250,6 +250,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    ctx.ransac_prune_stats(reset=True)
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -260,6 +261,7 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
     value = world * P * args.steps / (ms_total * 1e-3)
+    evals_done, evals_full = ctx.ransac_prune_stats()
 
     # sanity: the timed path produced real results
     res = res_d.cpu().numpy().view(PAIR_RESULT_DTYPE)
@@ -273,28 +275,38 @@ def main():
     torch.cuda.synchronize(dev)
     kt = {name: ctx.profile_ms(name) for name in ("expand", "hamming", "knnfix", "finish", "sample", "solve", "score", "select")}
     ctx.profile(False)
-    # k_score: profile it over several launches of the timed workload for the roofline figure
-    score_ms = []
+    # the two heavy stages over several profiled passes of the timed workload (events inside the library, launching stream)
+    score_ms, ham_ms = [], []
     for _ in range(3):
         ctx.profile(True)
         step_device()
         torch.cuda.synchronize(dev)
         score_ms.append(ctx.profile_ms("score"))
+        ham_ms.append(ctx.profile_ms("hamming"))
         ctx.profile(False)
-    score_ms_avg = float(np.mean(score_ms))
+    score_ms_avg, ham_ms_avg = float(np.mean(score_ms)), float(np.mean(ham_ms))
     peak, bf16_peak, peak_src = measured_peaks()
-    evals = float(args.hyps) * float(sum_tent)                    # (hypothesis, match) evaluations per launch
-    logical_bytes = 16.0 * evals + 36.0 * args.hyps * P + 8.0 * args.hyps * P
-    achieved = logical_bytes / (score_ms_avg * 1e-3) / 1e9
-    roofline = {"kernel": "k_count (RANSAC residual / inlier scoring of every hypothesis over every match)", "bound": "hbm",
-                "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("k_count", P, k, args.hyps),
-                "peak_source": peak_src, "evals_per_launch": evals, "ms_per_launch": score_ms_avg,
-                "hypotheses_scored_per_s": args.hyps * P / (score_ms_avg * 1e-3),
-                "note": "logical bytes = 16 B x hypotheses x matches (SURVEY 8d); tiles are L2/smem resident so DRAM "
-                        "traffic is far lower and the kernel is FP32-issue bound (DESIGN.md); residual sums are computed "
-                        "afterwards only for the hypotheses tied at the largest count (k_select)"}
+    # dominant kernel of the step: the tensor-core matcher
+    roofline = hamming_roofline(P, k, ham_ms_avg, bf16_peak, peak_src)
+    if roofline is not None:
+        roofline["traffic"] = ncu_traffic("k_knn2_tc4", P, k, args.hyps)
+    # second stage: RANSAC inlier counting. SURVEY 8d's unit is 16 B per (hypothesis, match) evaluation; the tiles live in
+    # shared memory / L2 and the stage is bound by the FP32 pipe, and the bounded counting performs only part of the
+    # evaluations a full pass would (the rest provably cannot change the winner), so both figures are given.
+    evals = float(args.hyps) * float(sum_tent)
+    frac_done = (evals_done / evals_full) if evals_full else None
+    counting = {"kernels": "k_bq_init + k_count_queue (persistent, work queue; packed fp32 residual with exact fallback)",
+                "ms_per_step": score_ms_avg, "evaluations_full": evals,
+                "fraction_evaluated": frac_done,
+                "evaluations_per_s": (evals * frac_done / (score_ms_avg * 1e-3)) if frac_done else None,
+                "hypotheses_decided_per_s": args.hyps * P / (score_ms_avg * 1e-3),
+                "logical_GBps_full_pass_equivalent": (16.0 * evals) / (score_ms_avg * 1e-3) / 1e9,
+                "hbm_peak_GBps": peak,
+                "dram_traffic_full_count_kernel": ncu_traffic("k_count", P, k, args.hyps),
+                "note": "a hypothesis is abandoned only when its count so far plus every match it has not seen is below a "
+                        "count another hypothesis is known to reach: winner, count, score and mask are bit-identical to "
+                        "counting everything (tests/test_gpu_bounded_count.py); VB_RANSAC_PRUNE=0 runs the full count "
+                        "(k_count2, 4.05 ms on this workload)"}
     step_ms = ms_total / args.steps
     shares = {n: (v / step_ms if v and v > 0 else None) for n, v in kt.items()}
 
@@ -347,7 +359,9 @@ def main():
                 "config": workload_config(args, P), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "kernel_ms": kt, "kernel_share_of_step": shares,
-                "hamming": hamming_roofline(P, k, kt["hamming"], bf16_peak, peak_src),
+                "counting": counting,
+                "bounded_counting": {"evaluations_done": evals_done, "evaluations_full": evals_full,
+                                     "fraction": (evals_done / evals_full) if evals_full else None},
                 "single_pair_match_features_ms": single_ms,
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
@@ -363,7 +377,7 @@ def main():
 
 
 def hamming_roofline(P, k, ms, bf16_peak, peak_src):
-    """Second kernel of the step: k_knn2_tc4, tensor-pipe work. Algorithmic work = 2 * 256 flop per descriptor pair
+    """Dominant kernel of the step: k_knn2_tc4, tensor-pipe work. Algorithmic work = 2 * 256 flop per descriptor pair
     (256-term +-1 dot product). The pipe it runs on is the fp4 one (kind::mxf4, K = 64 per UMMA): peak = 4 x the measured
     dense bf16 figure (K = 16 per UMMA on the same pipe)."""
     if not ms or ms <= 0:

@@ -150,6 +150,11 @@ int vb_ransac_counts(vb_ctx *ctx, const float *corr, uint32_t m, const float *F,
                      int32_t *n_inliers);
 int vb_ransac_counts_d(vb_ctx *ctx, const float *corr_d, uint32_t m, const float *F_d, uint32_t h, float threshold,
                        int32_t *n_inliers_d);
+/* Work done by the pair pipeline's bounded counting since the context was created (or last reset): hypothesis x match
+ * evaluations actually performed, and the number a full evaluation of every hypothesis on every match would have taken
+ * (find_fundamental's loop, :52-64). A hypothesis is abandoned only when its count so far plus every match it has not seen
+ * is below a count another hypothesis is known to reach, so the winner, its count, score and mask are unaffected. */
+int vb_ransac_prune_stats(vb_ctx *ctx, uint64_t *evaluated, uint64_t *total, int reset);
 /* The 8-point solve alone (compute_fundamental, :69-103) for h minimal samples: p1set/p2set [h][8][2]. */
 int vb_ransac_solve8(vb_ctx *ctx, const float *p1set, const float *p2set, uint32_t h, float *F);
 

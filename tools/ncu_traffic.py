@@ -22,5 +22,12 @@ for r in rows[2:]:
                 {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[units[ix["gpu__time_duration.sum"]]],
                 "source": os.path.basename(rep) + " (ncu --set full --clock-control none)"}
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-json.dump(res, open(os.path.join(root, "profiles", "ncu_traffic.json"), "w"), indent=1)
+path = os.path.join(root, "profiles", "ncu_traffic.json")
+try:
+    old = json.load(open(path))   # keep the entries of kernels this report does not contain
+except Exception:
+    old = {}
+old.update(res)
+res = old
+json.dump(res, open(path, "w"), indent=1)
 print(json.dumps(res, indent=1))

@@ -42,7 +42,7 @@ EXPORTS = [
     "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_build_batch_d", "vb_kdtree_free_batch", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
-    "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
+    "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
     "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms",
 ]
 
@@ -97,6 +97,7 @@ def load_library() -> C.CDLL:
     L.vb_ransac_score_d.argtypes = [vp, vp, u32, vp, u32, f32, vp, vp]
     L.vb_ransac_counts.argtypes = [vp, vp, u32, vp, u32, f32, vp]
     L.vb_ransac_counts_d.argtypes = [vp, vp, u32, vp, u32, f32, vp]
+    L.vb_ransac_prune_stats.argtypes = [vp, vp, vp, C.c_int]
     L.vb_ransac_solve8.argtypes = [vp, vp, vp, u32, vp]
     L.vb_ransac_sample_sets.argtypes = [vp, u32, C.c_int, u32, u32, vp]
     L.vb_ransac_residual.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp, f32, vp, C.POINTER(i32), C.POINTER(f32)]
@@ -258,6 +259,12 @@ class Context:
         cnt = np.zeros(len(F), np.int32)
         self._chk(self.L.vb_ransac_counts(self.h, _ptr(corr), len(corr), _ptr(F), len(F), thr, _ptr(cnt)))
         return cnt
+
+    def ransac_prune_stats(self, reset=False):
+        """(evaluations performed, evaluations a full count would take) of the pipeline's bounded counting so far."""
+        ev, tot = C.c_uint64(0), C.c_uint64(0)
+        self._chk(self.L.vb_ransac_prune_stats(self.h, C.byref(ev), C.byref(tot), 1 if reset else 0))
+        return ev.value, tot.value
 
     def ransac_solve8(self, p1set, p2set):
         p1set, p2set = _f32(p1set).reshape(-1, 8, 2), _f32(p2set).reshape(-1, 8, 2)
