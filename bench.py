@@ -110,11 +110,13 @@ def measured_peaks():
 
 def ncu_traffic(kernel, pairs, kpts, hyps):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of
-    this same workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), or None when the shapes differ."""
+    this same workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), or None when the shapes differ. The
+    captured launch may cover a different number of pairs than the launch bench.py times (every pair moves the same bytes:
+    its two frames' operands in, its partial results out), so the figure is scaled to `pairs`."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
-        if (d["pairs"], d["kpts"], d["hyps"]) == (pairs, kpts, hyps):
-            return float(d["dram_bytes_per_launch"])
+        if (d["kpts"], d["hyps"]) == (kpts, hyps) and d["pairs"] > 0:
+            return float(d["dram_bytes_per_launch"]) * pairs / d["pairs"]
     except Exception:
         pass
     return None
@@ -286,29 +288,34 @@ def main():
         ctx.profile(False)
     score_ms_avg, ham_ms_avg = float(np.mean(score_ms)), float(np.mean(ham_ms))
     peak, bf16_peak, peak_src = measured_peaks()
+    # with the profiling brackets on, vb_pairs_run_d works in batches of 1 024 pairs and the brackets keep the last batch
+    P_prof = P - 1024 * ((P - 1) // 1024)
+    tent_prof = int(res["n_tentative"][P - P_prof:].sum())
     # dominant kernel of the step: the tensor-core matcher
-    roofline = hamming_roofline(P, k, ham_ms_avg, bf16_peak, peak_src)
+    roofline = hamming_roofline(P_prof, k, ham_ms_avg, bf16_peak, peak_src)
     if roofline is not None:
-        roofline["traffic"] = ncu_traffic("k_knn2_tc4", P, k, args.hyps)
+        roofline["traffic"] = ncu_traffic("k_knn2_tc4", P_prof, k, args.hyps)
+        roofline["pairs_per_launch"] = P_prof
     # second stage: RANSAC inlier counting. SURVEY 8d's unit is 16 B per (hypothesis, match) evaluation; the tiles live in
     # shared memory / L2 and the stage is bound by the FP32 pipe, and the bounded counting performs only part of the
     # evaluations a full pass would (the rest provably cannot change the winner), so both figures are given.
-    evals = float(args.hyps) * float(sum_tent)
+    evals = float(args.hyps) * float(tent_prof)
     frac_done = (evals_done / evals_full) if evals_full else None
     counting = {"kernels": "k_bq_init + k_count_queue (persistent, work queue; packed fp32 residual with exact fallback)",
-                "ms_per_step": score_ms_avg, "evaluations_full": evals,
+                "ms_per_launch": score_ms_avg, "pairs_per_launch": P_prof, "evaluations_full": evals,
                 "fraction_evaluated": frac_done,
                 "evaluations_per_s": (evals * frac_done / (score_ms_avg * 1e-3)) if frac_done else None,
-                "hypotheses_decided_per_s": args.hyps * P / (score_ms_avg * 1e-3),
+                "hypotheses_decided_per_s": args.hyps * P_prof / (score_ms_avg * 1e-3),
                 "logical_GBps_full_pass_equivalent": (16.0 * evals) / (score_ms_avg * 1e-3) / 1e9,
                 "hbm_peak_GBps": peak,
-                "dram_traffic_full_count_kernel": ncu_traffic("k_count", P, k, args.hyps),
+                "dram_traffic_full_count_kernel": ncu_traffic("k_count", P_prof, k, args.hyps),
                 "note": "a hypothesis is abandoned only when its count so far plus every match it has not seen is below a "
                         "count another hypothesis is known to reach: winner, count, score and mask are bit-identical to "
                         "counting everything (tests/test_gpu_bounded_count.py); VB_RANSAC_PRUNE=0 runs the full count "
                         "(k_count2, 4.05 ms on this workload)"}
     step_ms = ms_total / args.steps
-    shares = {n: (v / step_ms if v and v > 0 else None) for n, v in kt.items()}
+    # kernel_ms covers the last batch of P_prof pairs; its share of the step is scaled to the step's P pairs
+    shares = {n: (v * (P / P_prof) / step_ms if v and v > 0 else None) for n, v in kt.items()}
 
     # ---- end to end through the host-pointer ABI call -------------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
