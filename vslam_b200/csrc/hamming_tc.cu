@@ -487,17 +487,23 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
 }
 
-// Sixteen lanes per query: merge the column parts into (best group, best other group), evaluate the 16 descriptors
-// of those two 8-column groups with XOR + POPC on the original descriptors, and keep their two smallest
-// (distance, index) keys. out[p][q] = final (best, second).
+// LANES lanes per query: merge the column parts into (best group, best other group) and evaluate candidates with XOR + POPC
+// on the original descriptors. out[p][q] = final (best, second) keys.
+//   LANES = 16: the 16 descriptors of both 8-column groups, their two smallest (distance, index) keys — knnMatch's pair,
+//               second index included (the vb_knn2_hamming entry points).
+//   LANES = 8:  the best group only. A group key carries the group's best DISTANCE exactly (it is the accumulator's
+//               maximum), so the second neighbour's distance is min(second smallest in the best group, the other group's
+//               key distance) without reading that group; only the second neighbour's index stays unknown (the key keeps
+//               the group's first column), and match_features (src/Frame.cpp:91-95) never looks at it. Half the bytes.
+template <int LANES>
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
                                                      size_t stride_words, uint32_t n1, uint32_t n2, uint32_t nparts,
                                                      const uint2 *__restrict__ part, uint2 *__restrict__ out) {
-    static_assert(TC_GROUP == 8, "two groups of eight lanes per query");
-    const uint32_t sub = threadIdx.x & 15;
-    const uint32_t q = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4), p = blockIdx.y;
+    static_assert(TC_GROUP == 8 && (LANES == 8 || LANES == 16), "groups of eight lanes per query");
+    const uint32_t sub = threadIdx.x & (LANES - 1);
+    const uint32_t q = blockIdx.x * (blockDim.x / LANES) + (threadIdx.x / LANES), p = blockIdx.y;
     const bool live = q < n1;
-    uint32_t key = 0xffffffffu;
+    uint32_t key = 0xffffffffu, other = 0xffffffffu;
     if (live) {
         uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;   // group keys: (best distance in the group) << 22 | first column
         for (uint32_t s = 0; s < nparts; s++) {
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
         }
         const uint32_t gk = (sub < 8) ? k1 : k2;
         const uint32_t col = (gk & KNN_IDX_MASK) + (sub & 7);
+        if (LANES == 8) other = k2;
         if (gk != 0xffffffffu && col < n2) {
             const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
             const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
@@ -519,10 +526,10 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
     }
     uint32_t best = key;
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    uint32_t second = (key == best) ? 0xffffffffu : key;   // keys of distinct columns are distinct
+    for (int o = 1; o < LANES; o <<= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    uint32_t second = (key == best) ? other : key;   // keys of distinct columns are distinct
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
+    for (int o = 1; o < LANES; o <<= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
     if (live && sub == 0) out[(size_t)p * n1 + q] = make_uint2(best, second);
 }
 
@@ -545,7 +552,7 @@ static bool hamming_tc_use_fp4() {
 }
 
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
-                      const uint2 **final_part) {
+                      const uint2 **final_part, bool need_second_index) {
     const bool fp4 = hamming_tc_use_fp4();
     if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -602,7 +609,11 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
-    k_knn2_tc_fix<<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+    static const bool fix8 = !(getenv("VB_TC_FIX8") && atoi(getenv("VB_TC_FIX8")) == 0);
+    if (need_second_index || !fix8)
+        k_knn2_tc_fix<16><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+    else
+        k_knn2_tc_fix<8><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     ctx->prof_end("knnfix");
     ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
