@@ -166,20 +166,22 @@ def run_reference(args, rank, world):
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-            "config": workload_config(args, sample),
+            "vs_baseline": None, "dtype": "u8 XOR+popcount Hamming + f32/f64 residual (host cores)", "data": "synthetic",
+            "config": workload_config(args, sample, device=False),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port",
                              "sample": f"{sample} pairs per step x {args.steps} steps, OpenMP over pairs"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, pairs_per_rank):
+def workload_config(args, pairs_per_rank, device=True):
+    mb = (pairs_per_rank + 1) * args.kpts * 40 / 1e6
     return {"workload": "BASELINE configs[1]: frame pairs of 5000 keypoints, 256-bit binary descriptors, "
                         "1024 RANSAC hypotheses (synthetic forward-motion sequence, SURVEY 8d C2/C4)",
             "kpts": args.kpts, "descriptor_bits": 256, "hypotheses": args.hyps, "threshold": args.threshold, "ratio": 0.7,
             "pairs_per_step_per_gpu": pairs_per_rank,
-            "l2": "per-rank inputs %.0f MB > 126 MB L2; no explicit flush" % ((pairs_per_rank + 1) * args.kpts * 40 / 1e6)}
+            "l2": ("per-rank inputs %.0f MB %s 126 MB L2; no explicit flush" % (mb, ">" if mb > 126 else "<")) if device
+                  else "host run: bounded sample of the same sequence, %.0f MB of inputs per step" % mb}
 
 
 # ---------------------------------------------------------------------------------------------------
