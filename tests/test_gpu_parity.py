@@ -568,7 +568,8 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
 
 def test_scalar_fallback_kernels_in_subprocess():
     """k_count<2> / k_score<2> (the scalar-instruction versions kept behind VB_COUNT_PACKED=0 / VB_SCORE_PACKED=0, read once per
-    process) and the fp8 matcher (VB_HAMMING_FP4=0) still agree with the oracle."""
+    process), the fp8 matcher (VB_HAMMING_FP4=0) and the two-group fix pass on the match path (VB_TC_FIX8=0) still agree with the
+    oracle."""
     import os
     import subprocess
     import sys
@@ -597,6 +598,8 @@ o = orc.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], 0.7, 8, 256, 10.0
 assert g["n"] == o["n"] and np.array_equal(g["matches"], o["matches"]) and np.array_equal(g["F"].view(np.uint32), o["F"].view(np.uint32))
 print("fallback kernels ok")
 """ % (root, os.path.join(root, "tests"))
-    env = dict(os.environ, VB_COUNT_PACKED="0", VB_SCORE_PACKED="0", VB_HAMMING_FP4="0")
-    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "fallback kernels ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # second run: default kernels, but the matcher's fix pass reading both candidate groups on the match path too
+    for extra in (dict(VB_COUNT_PACKED="0", VB_SCORE_PACKED="0", VB_HAMMING_FP4="0"), dict(VB_TC_FIX8="0")):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "fallback kernels ok" in r.stdout, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
