@@ -109,3 +109,38 @@ def test_bounded_counting_single_problem_entry_point(ctx, oracle, monkeypatch):
         assert np.array_equal(bits(g["score"]), bits(o["score"]))
         assert np.array_equal(bits(g["F"]), bits(o["F"]))
         assert np.array_equal(g["mask"], o["mask"])
+
+
+def test_bounded_counting_default_rule_device_batch(ctx, monkeypatch):
+    """vb_pairs_run_d on a device-resident batch large enough for the default rule (VB_RANSAC_PRUNE unset) and for the two
+    batch halves on two streams: same results as the full count; and duplicated / degenerate correspondences in the batch
+    (every hypothesis ties, or no hypothesis has an inlier) do not disturb the queue."""
+    import ctypes as C
+    import torch
+    from vslam_b200.lib import PAIR_RESULT_DTYPE
+    nframes, k = 701, 400
+    pts, desc = synth.sequence(nframes, k, 77, noise_px=0.5, outlier_frac=0.3)
+    pts[100:103] = pts[100]                     # identical frames: noise-free duplicates, every hypothesis ties
+    desc[100:103] = desc[100]
+    pts[300] = 5.0                              # all keypoints of a frame in one place: degenerate models
+    prm = ctx.params(0.7, 8, 512, 10.0, 5)
+    P = nframes - 1
+    pts_d, desc_d = torch.from_numpy(pts).cuda(), torch.from_numpy(desc).cuda()
+
+    def run():
+        res = torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        out = torch.zeros((P, k, 2), dtype=torch.int32, device="cuda")
+        ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, C.c_void_p(pts_d.data_ptr()), C.c_void_p(desc_d.data_ptr()), nframes, k, 32,
+                                      C.byref(prm), C.c_void_p(res.data_ptr()), C.c_void_p(out.data_ptr())))
+        ctx.synchronize()
+        return res.cpu().numpy().view(PAIR_RESULT_DTYPE), out.cpu().numpy()
+
+    monkeypatch.setenv("VB_RANSAC_PRUNE", "0")
+    ref, mref = run()
+    monkeypatch.delenv("VB_RANSAC_PRUNE")
+    ctx.ransac_prune_stats(reset=True)
+    got, mgot = run()
+    ev, tot = ctx.ransac_prune_stats()
+    assert 0 < ev < tot            # the default rule took the bounded path and abandoned something
+    assert_same_results(got, mgot, ref, mref)
+    assert (got["status"] == 0).sum() > 600
