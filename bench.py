@@ -354,12 +354,25 @@ def main():
         vq, _, _, _ = cpu_pairs_per_s(orc, pts, desc, int(min(P, max(cores, 8))), args.hyps, args.threshold, 1, threads=cores)
         sample = int(min(P, max(cores, 8, vq * 12.0)))   # about 10 s of host work, never more than the step itself
         vN, used, dtN, _ = cpu_pairs_per_s(orc, pts, desc, sample, args.hyps, args.threshold, 1, threads=cores)
-        # parity spot check of the timed GPU output against the same oracle (first pair)
-        o = orc.match_features(pts[0], desc[0], pts[1], desc[1], 0.7, 8, args.hyps, args.threshold, 1)
-        parity = bool(o["n"] == int(res["n_matches"][0]) and o["best"] == int(res["best_hyp"][0]))
+        # parity spot check of the timed GPU output (device-resident results, and the matches of the end-to-end call) against
+        # the same oracle: first pair and five more spread over the step — counts, winner, every match, F bit for bit
+        out_e = out_h.numpy()
+        sample_pairs = sorted(set([0, 1, P // 3, P // 2, (2 * P) // 3, P - 1]))
+        n_same = 0
+        for i in sample_pairs:
+            o = orc.match_features(pts[i], desc[i], pts[i + 1], desc[i + 1], 0.7, 8, args.hyps, args.threshold, 1 + i)
+            same = (o["n"] == int(res["n_matches"][i]) == int(res_e["n_matches"][i]) and o["best"] == int(res["best_hyp"][i])
+                    and o["n_tentative"] == int(res["n_tentative"][i])
+                    and np.array_equal(out_e[i, :max(o["n"], 0)], o["matches"])
+                    and np.array_equal(np.ascontiguousarray(res["F"][i], np.float32).view(np.uint32).reshape(-1),
+                                       np.ascontiguousarray(o["F"], np.float32).view(np.uint32).reshape(-1)))
+            n_same += int(bool(same))
+            if i == 0:
+                parity = bool(same)
         cpu = {"value": vN, "unit": UNIT, "cores": used, "kind": "port",
                "sample": f"{sample} pairs over {used} OpenMP threads in {dtN:.1f} s (oracle C port, -O3 -march=native)",
-               "single_thread_pairs_per_s": v1, "host_cpus": cores, "gpu_matches_oracle_on_pair0": parity}
+               "single_thread_pairs_per_s": v1, "host_cpus": cores, "gpu_matches_oracle_on_pair0": parity,
+               "gpu_matches_oracle_on_sampled_pairs": "%d of %d" % (n_same, len(sample_pairs))}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
