@@ -70,7 +70,10 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     // Batches alternate between the context and its twin (own stream + workspaces) so that the tail of one batch's kernels
     // overlaps the head of the next one's; the twin starts after everything already queued on the caller's stream and
     // the caller's stream ends by waiting for the twin.
-    static const bool use_twin = !(getenv("VB_PAIRS_TWIN") && atoi(getenv("VB_PAIRS_TWIN")) == 0);
+    // Off by default since the counting stage became one persistent kernel per batch: its fixed cost (the rounds of the last
+    // problems, ~0.09 ms) is paid per launch and two halves no longer overlap anything else — 5.13 ms whole against 5.20 ms
+    // split per 1 024 pairs. VB_PAIRS_SPLIT=1 restores the split.
+    static const bool use_twin = getenv("VB_PAIRS_SPLIT") && atoi(getenv("VB_PAIRS_SPLIT")) != 0;
     // (not while the profiling brackets are on: they time the context's own stream, one whole batch at a time)
     const bool split = use_twin && !ctx->profile && P >= 512;
     const uint32_t batch = split ? (P < 2 * PAIRS_MAX_BATCH ? (P + 1) / 2 : PAIRS_MAX_BATCH) : PAIRS_MAX_BATCH;
