@@ -171,7 +171,7 @@ typedef struct {
 } vb_pair_params;
 
 typedef struct {
-    int32_t status;      /* VB_OK, VB_ERR_TOO_FEW or VB_ERR_NO_MODEL for this pair */
+    int32_t status;      /* VB_OK, VB_ERR_TOO_FEW or VB_ERR_NO_MODEL for this pair (VB_ERR_CUDA: internal failure, no result) */
     int32_t n_tentative; /* matches surviving the ratio test */
     int32_t n_matches;   /* final (RANSAC inlier) matches written for this pair */
     int32_t best_hyp;

@@ -54,6 +54,7 @@ struct RansacSelectArgs {
     int prefolded;          // cnt/score already hold the folded totals (k_fold ran first)
     int lazy;               // counts came from k_count: no residual sums; k_select scores the tied hypotheses itself
     uint32_t *tied;         // [P][H] scratch list of tied hypotheses (lazy mode)
+    const unsigned int *queue_timeouts;   // bounded counting: non-zero if a work-queue wait gave up (counts incomplete), or nullptr
 };
 
 int ransac_plan(vb_ctx *ctx, uint32_t P, uint32_t mcap, uint32_t m_upper, uint32_t H, int min_items, RansacPlan *pl);
