@@ -260,6 +260,58 @@ def test_knn2_hamming_vs_oracle(ctx, oracle, n1, n2, nbytes):
         assert np.array_equal(ctx.match_hamming(d1, d2, ratio), oracle.match_hamming(d1, d2, ratio))
 
 
+TC_SHAPES = [(1, 2), (1, 7), (3, 8), (5, 9), (255, 239), (256, 240), (257, 241), (1000, 129), (1000, 479), (255, 481),
+             (256, 8), (300, 1000), (3000, 239), (3000, 241), (1000, 16383), (2500, 16384), (513, 720), (100, 961)]
+
+
+@pytest.mark.parametrize("n1,n2", TC_SHAPES)
+def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, monkeypatch, n1, n2):
+    """The tcgen05 matcher (k_knn2_tc4 + k_knn2_tc_fix) forced onto shapes the size heuristic would send to the popcount
+    kernel: n1 != n2, n2 around the 240-column tile and the 8-column group, n2 < one tile, n1 around the 256-query block, the
+    n2 = 16 384 key limit; duplicated train rows straddling group and tile boundaries (ties to the lower index).
+    BFMatcher knnMatch k = 2 order, reference src/Frame.cpp:83-85; ratio test :91."""
+    monkeypatch.setenv("VB_HAMMING_TC", "1")
+    rng = np.random.default_rng(n1 * 131 + n2)
+    d2 = synth.random_descriptors(rng, n2)
+    d1 = synth.random_descriptors(rng, n1)
+    k = min(n1, n2) // 2
+    if k:
+        d1[:k] = synth.flip_bits(rng, d2[rng.permutation(n2)[:k]], 12)
+    # equal rows across a group boundary (7|8), a tile boundary (239|240) and the last valid column
+    for a, b in ((7, 8), (0, 15), (239, 240), (232, 479), (n2 - 1, 3), (n2 - 2, n2 - 9)):
+        if 0 <= a < n2 and 0 <= b < n2 and a != b:
+            d2[max(a, b)] = d2[min(a, b)]
+    if n1 > 4 and n2 > 16:
+        d1[1] = d2[7]      # zero distance to a duplicated pair
+        d1[2] = d2[n2 - 1]
+    idx, dist = ctx.knn2_hamming(d1, d2)
+    oidx, odist = oracle.knn2_hamming(d1, d2)
+    assert np.array_equal(dist, odist)
+    assert np.array_equal(idx, oidx)
+    for ratio in (0.7, 1.0):
+        assert np.array_equal(ctx.match_hamming(d1, d2, ratio), oracle.match_hamming(d1, d2, ratio))
+
+
+@pytest.mark.parametrize("k", [241, 600, 1000])
+def test_tensor_path_whole_pair_and_sequence_edge_shapes(ctx, oracle, monkeypatch, k):
+    """match_features (P = 1) and a 4-frame sequence (P = 3, shared expanded frames) through the forced tensor path at sizes
+    that leave a ragged last tile / query block."""
+    monkeypatch.setenv("VB_HAMMING_TC", "1")
+    pts, desc = synth.sequence(4, k, k)
+    prm = ctx.params(0.7, 8, 64, 10.0, 77)
+    res, out = ctx.pairs_run(pts, desc, prm)
+    for i in range(3):
+        o = oracle.match_features(pts[i], desc[i], pts[i + 1], desc[i + 1], 0.7, 8, 64, 10.0, 77 + i)
+        assert res["n_tentative"][i] == o["n_tentative"] and res["n_matches"][i] == max(o["n"], 0)
+        if o["n"] > 0:
+            assert np.array_equal(out[i, :o["n"]], o["matches"]) and np.array_equal(bits(res["F"][i]), bits(o["F"].reshape(-1)))
+    g = ctx.match_features(pts[0], desc[0], pts[2][:k - 37], desc[2][:k - 37], prm)     # n1 != n2
+    o = oracle.match_features(pts[0], desc[0], pts[2][:k - 37], desc[2][:k - 37], 0.7, 8, 64, 10.0, 77)
+    assert g["n_tentative"] == o["n_tentative"] and g["n"] == max(o["n"], 0)
+    if o["n"] > 0:
+        assert np.array_equal(g["matches"], o["matches"]) and np.array_equal(bits(g["F"]), bits(o["F"]))
+
+
 def test_hamming_too_few_train(ctx):
     from vslam_b200.lib import VbError
     d = np.zeros((4, 32), np.uint8)
