@@ -26,6 +26,7 @@
 #ifndef VSLAM_B200_H
 #define VSLAM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -191,6 +192,55 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
                  const vb_pair_params *params, vb_pair_result *results, int32_t *out_matches);
 int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint32_t nframes, uint32_t k,
                    uint32_t bytes, const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Streaming submission with a compact result download — for callers that process one sequence after another (the
+ * reference's main loop calls match_features once per frame, src/vslam.cpp:92; a batch of frames is one submission).
+ * Up to two submissions per context are in flight: the upload of the next one and the download of the previous one
+ * overlap the kernels of the current one. All pointers are HOST pointers and must stay valid until the ticket has been
+ * waited for; copies overlap with compute only when they are pinned (vb_host_alloc / vb_host_register).
+ *   results        [nframes-1]
+ *   match_offsets  [nframes-1]  index (in matches, not bytes) of pair i's first match inside matches16
+ *   matches16      [cap_matches][2]  (query, train) keypoint indices as uint16 — what match_features appends to
+ *                  frame1.matches (src/Frame.cpp:98-102); pair i owns results[i].n_matches entries from match_offsets[i].
+ *                  Requires k <= 65535. match_offsets == matches16 == NULL skips the match download.
+ * vb_pairs_wait returns VB_ERR_CAPACITY (and the required size in *total_matches) when cap_matches is too small; the
+ * vb_pair_result entries are valid in that case. Same results, bit for bit, as vb_pairs_run.
+ * ---------------------------------------------------------------------------------------------- */
+int vb_pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                    const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,
+                    uint64_t cap_matches, int *ticket);
+int vb_pairs_wait(vb_ctx *ctx, int ticket, uint64_t *total_matches);
+/* submit + wait */
+int vb_pairs_run_compact(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                         const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,
+                         uint64_t cap_matches, uint64_t *total_matches);
+/* Pinned (page-locked, portable across contexts) host memory, or pinning of memory the caller already owns. */
+int vb_host_alloc(size_t bytes, void **out);
+int vb_host_free(void *p);
+int vb_host_register(void *p, size_t bytes);
+int vb_host_unregister(void *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Several GPUs of one box from ONE process: a vb_multi owns one host thread + one context + its own streams
+ * per listed device. The nframes-1 pairs of a sequence are cut into contiguous ranges, one per GPU (one-frame halo);
+ * every GPU downloads straight into the caller's arrays at its range's position, which is the host gather — there is no
+ * exchange between GPUs, hence no collective. Pair i samples with std::mt19937(seed0 + i) on whichever GPU it runs, so
+ * the output does not depend on the device list. Arguments as vb_pairs_submit, except that matches16 must have room for
+ * (nframes-1) * k matches: the range of GPU g starts at match index first_pair(g) * k and is packed from there
+ * (match_offsets[] holds the absolute start of every pair).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vb_multi vb_multi;
+int vb_multi_create(const int *devices, uint32_t ndev, vb_multi **out);
+int vb_multi_destroy(vb_multi *m);
+uint32_t vb_multi_device_count(const vb_multi *m);
+int vb_multi_pairs_submit(vb_multi *m, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                          const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets,
+                          uint16_t *matches16, uint64_t cap_matches, int *ticket);
+int vb_multi_pairs_wait(vb_multi *m, int ticket, uint64_t *total_matches);
+int vb_multi_pairs_run(vb_multi *m, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
+                       const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,
+                       uint64_t cap_matches, uint64_t *total_matches);
 
 /* ------------------------------------------------------------------------------------------------
  * Search by projection — replaces the loop at reference src/vslam.cpp:129-161 together with orb_distance

@@ -648,6 +648,21 @@ void vbo_extract_rt(const float *F, const float *K, float *R, float *t) {
     float E[9], U[9], D[3], Vt[9];
     vbo_essential(F, K, E);
     vbo_svd3x3(E, U, D, Vt);                                   /* :7 */
+    /* An exactly rank-2 E (e.g. F = [t]x with K = I) has a singular value of exactly 0, for which vbo_svd3x3 returns a zero
+     * column of U (it cannot divide by 0). cv::SVD::compute with FULL_UV completes the basis instead, so U.col(2) is the
+     * unit null vector of E^T (up to sign, which :31 fixes). Same here: the normalised cross product of the first two
+     * columns, in double, when the third column is not a unit vector or its singular value is below 2^-40 of the largest
+     * (the Jacobi sweep stops at 2^-52 relative, so such a column is rounding noise, not a direction). */
+    {
+        const double n2 = ((double)U[2] * U[2] + (double)U[5] * U[5]) + (double)U[8] * U[8];
+        if (!(n2 >= 0.5) || !(D[2] > D[0] * 9.094947017729282e-13f)) {
+            const double c0 = (double)U[3] * U[7] - (double)U[6] * U[4];
+            const double c1 = (double)U[6] * U[1] - (double)U[0] * U[7];
+            const double c2 = (double)U[0] * U[4] - (double)U[3] * U[1];
+            const double ci = 1.0 / sqrt((c0 * c0 + c1 * c1) + c2 * c2);
+            U[2] = (float)(c0 * ci); U[5] = (float)(c1 * ci); U[8] = (float)(c2 * ci);
+        }
+    }
     for (int i = 0; i < 3; i++) t[i] = U[i * 3 + 2];           /* :9  U.col(2) */
     const double nrm = sqrt(((double)t[0] * t[0] + (double)t[1] * t[1]) + (double)t[2] * t[2]); /* cv::norm: double */
     const double inv = 1.0 / nrm;                              /* :11 Mat /= s scales by 1/s in double */

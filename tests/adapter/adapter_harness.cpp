@@ -122,6 +122,18 @@ int main(int argc, char **argv) {
         for (size_t k = 0; k < again.size(); k++) if (again[k] != rv[0][k]) { fprintf(stderr, "re-import order\n"); return 3; }
     }
     free(kd.root);
+    // the same struct constructed a second time: `size` is now n2 + n1 (the reference never resets it, src/KDTree.cpp:16)
+    // while root holds n1 nodes — a re-import after eviction must count the nodes, not trust `size`
+    construct_kdtree(kd, p1);
+    if ((int)kd.size != n1 + n2) { fprintf(stderr, "size must accumulate like the reference's\n"); return 3; }
+    if (nq) {
+        std::vector<cv::Point2f> before = radius_search(kd, q[0], radius * 4);
+        vslam_b200_kdtree_release(kd.root);
+        std::vector<cv::Point2f> after = radius_search(kd, q[0], radius * 4);
+        if (before.size() != after.size()) { fprintf(stderr, "re-import of a twice-constructed struct changed the result\n"); return 3; }
+        for (size_t k = 0; k < after.size(); k++) if (before[k] != after[k]) { fprintf(stderr, "re-import (2) order\n"); return 3; }
+    }
+    free(kd.root);
 
     // ---- index tree (what Frame carries) ----
     frame_kdtree fk;

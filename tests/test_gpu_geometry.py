@@ -31,6 +31,22 @@ def test_extract_rt_bit_exact_vs_oracle_and_cv2_E(ctx, oracle):
         assert np.array_equal(_bits(E[i]), _bits(oracle.essential(F[i], G["K"])))
 
 
+def test_extract_rt_sweep_and_singular_bit_exact(ctx, oracle):
+    """The 2 000-motion sweep (all rotation angles) and the exactly singular E cases (zero singular value: U completed by a
+    cross product, src/helpers.cpp:7-9) — GPU == oracle bit for bit, no NaN."""
+    SW = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_rt_sweep_cv2_4_13.npz"))
+    R, t, _ = ctx.extract_rt(SW["F"], SW["K"])
+    for i in range(0, len(R), 7):
+        Ro, to = oracle.extract_rt(SW["F"][i], SW["K"])
+        assert np.array_equal(_bits(R[i]), _bits(Ro)) and np.array_equal(_bits(t[i]), _bits(to)), i
+    Ki = np.eye(3, dtype=np.float32)
+    R, t, _ = ctx.extract_rt(SW["sing_F"], Ki)
+    assert np.isfinite(R).all() and np.isfinite(t).all()
+    for i in range(len(R)):
+        Ro, to = oracle.extract_rt(SW["sing_F"][i], Ki)
+        assert np.array_equal(_bits(R[i]), _bits(Ro)) and np.array_equal(_bits(t[i]), _bits(to)), i
+
+
 def test_extract_rt_on_pipeline_output(ctx, oracle):
     """F as produced by the pair pipeline -> R, t close to the synthetic motion's direction."""
     from vslam_b200 import synth

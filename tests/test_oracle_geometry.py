@@ -45,3 +45,59 @@ def test_triangulate_vs_cv2_and_ground_truth(oracle):
     eo = np.linalg.norm(P[:, :3] - X[:, :3], axis=1)
     er = np.linalg.norm(ref[:, :3] - X[:, :3], axis=1)
     assert np.median(eo) < 0.5 and abs(np.median(eo) - np.median(er)) < 1e-2
+
+
+SW = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_rt_sweep_cv2_4_13.npz"))
+
+
+def _candidates(oracle, F, K):
+    """R_1, R_2 of src/helpers.cpp:18-27 from the oracle's own SVD."""
+    U, D, Vt = oracle.svd3(oracle.essential(F, K))
+    W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float64)
+    out = []
+    for Wm in (W, W.T):
+        R = U.astype(np.float64) @ Wm @ Vt.astype(np.float64)
+        out.append(-R if np.linalg.det(R) < 0 else R)
+    return out
+
+
+def test_extract_rt_discrete_choice_sweep(oracle):
+    """2 000 motions, rotation angle uniform in [0, pi] (tests/golden/gen_golden_rt_sweep.py). `trace(R_1) < 0 ? R_2 : R_1`
+    (:29) swaps with the sign of a singular pair, so it is pinned only where exactly one candidate has a negative trace;
+    there the oracle must make cv2's choice (2e-4 on R's entries, 2e-4 on t up to the sign :31 leaves open when t_z ~ 0).
+    The twisted twin's trace is 2 (1 - cos th)(a.b)^2 - 1 (a = rotation axis, b = baseline direction), negative for every
+    rotation below 60 degrees, so every frame-to-frame motion is in the pinned set. Elsewhere the oracle returns one of cv2's
+    two candidates and the agreement rate is reported."""
+    K = SW["K"]
+    n_pinned = n_free = free_equal = 0
+    for F, R, t, a in zip(SW["F"], SW["R"], SW["t"], SW["angle"]):
+        Ro, to = oracle.extract_rt(F, K)
+        assert min(np.abs(to - t).max(), np.abs(to + t).max()) < 2e-4
+        R1, R2 = _candidates(oracle, F, K)
+        tr1, tr2 = np.trace(R1), np.trace(R2)
+        same = np.abs(Ro - R).max() < 2e-4
+        if (tr1 < -1e-3) != (tr2 < -1e-3) and min(abs(tr1), abs(tr2)) > 1e-3:
+            n_pinned += 1
+            assert same, (float(a), tr1, tr2)
+        else:
+            n_free += 1
+            free_equal += bool(same)
+            twin = R2 if np.abs(Ro - R1).max() < 1e-5 else R1
+            assert same or np.abs(twin - R).max() < 2e-4      # cv2 picked the other candidate of the same pair
+    print(f"pick pinned on {n_pinned} motions (all equal); convention-dependent on {n_free}, equal on {free_equal}")
+    assert n_pinned > 1400
+    small = SW["angle"] < 1.0
+    assert small.sum() > 500                                   # every motion below 60 degrees is in the pinned set
+    for F, R in zip(SW["F"][small], SW["R"][small]):
+        assert np.abs(oracle.extract_rt(F, K)[0] - R).max() < 2e-4
+
+
+def test_extract_rt_exactly_singular_essential(oracle):
+    """F = [t]x, K = I: E has a singular value of exactly 0. cv::SVD completes U; so must the oracle (no NaN, unit t)."""
+    Ki = np.eye(3, dtype=np.float32)
+    for F, R, t in zip(SW["sing_F"], SW["sing_R"], SW["sing_t"]):
+        Ro, to = oracle.extract_rt(F, Ki)
+        assert np.isfinite(Ro).all() and np.isfinite(to).all()
+        assert abs(float(np.linalg.norm(to.astype(np.float64))) - 1.0) < 1e-6
+        assert min(np.abs(to - t).max(), np.abs(to + t).max()) < 2e-6
+        assert np.abs(np.abs(Ro) - np.abs(R)).max() < 2e-6 and np.linalg.det(Ro.astype(np.float64)) > 0.999

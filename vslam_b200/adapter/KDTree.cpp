@@ -84,16 +84,35 @@ std::vector<float> flatten(const std::vector<cv::Point2f> &pts) {
     return f;
 }
 
-// Device tree for a value tree; imports it from the host nodes when the side table does not have it.
+// Number of nodes hanging off `root`, by walking the links. The struct's own `size` cannot be trusted: the reference (and
+// this adapter, to stay observably identical) only ever ADDS to it (src/KDTree.cpp:16), so a struct that was constructed
+// twice reports n1 + n2 while `root` holds n2 nodes.
+template <typename Node> uint32_t count_nodes(const Node *root) {
+    uint32_t n = 0;
+    std::vector<const Node *> st;
+    if (root) st.push_back(root);
+    while (!st.empty()) {
+        const Node *nd = st.back();
+        st.pop_back();
+        n++;
+        if (nd->left) st.push_back(nd->left);
+        if (nd->right) st.push_back(nd->right);
+    }
+    return n;
+}
+
+// Device tree for a value tree; imports it from the host nodes when the side table does not have it (evicted, or built by
+// other code). The nodes of a construct_kdtree result are one pre-order block, so root[0..n) is the whole tree.
 Entry &entry_for(const KDTree &t) {
     Table &tb = table();
     auto it = tb.map.find(t.root);
     if (it != tb.map.end()) { tb.touch(it->second, t.root); return it->second; }
-    std::vector<float> pre((size_t)t.size * 2);
-    for (uint32_t s = 0; s < t.size; s++) { pre[2 * s] = t.root[s].pt.x; pre[2 * s + 1] = t.root[s].pt.y; }
+    const uint32_t n = count_nodes(t.root);
+    std::vector<float> pre((size_t)n * 2);
+    for (uint32_t s = 0; s < n; s++) { pre[2 * s] = t.root[s].pt.x; pre[2 * s + 1] = t.root[s].pt.y; }
     vb_tree *dt = nullptr;
-    check(vb_kdtree_import(context(), pre.data(), nullptr, t.size, &dt), "vb_kdtree_import");
-    Entry &e = tb.put(t.root, dt, t.size);   // idx == slot, so slot_of stays empty (identity)
+    check(vb_kdtree_import(context(), pre.data(), nullptr, n, &dt), "vb_kdtree_import");
+    Entry &e = tb.put(t.root, dt, n);   // idx == slot, so slot_of stays empty (identity)
     return e;
 }
 
@@ -101,17 +120,18 @@ Entry &entry_for(const frame_kdtree &t, const std::vector<cv::Point2f> &points) 
     Table &tb = table();
     auto it = tb.map.find(t.root);
     if (it != tb.map.end()) { tb.touch(it->second, t.root); return it->second; }
-    std::vector<float> pre((size_t)t.size * 2);
-    std::vector<uint32_t> idx(t.size);
-    for (uint32_t s = 0; s < t.size; s++) {
+    const uint32_t n = count_nodes(t.root);
+    std::vector<float> pre((size_t)n * 2);
+    std::vector<uint32_t> idx(n);
+    for (uint32_t s = 0; s < n; s++) {
         const usize pi = t.root[s].pt_index;
         idx[s] = (uint32_t)pi;
         pre[2 * s] = points[pi].x;
         pre[2 * s + 1] = points[pi].y;
     }
     vb_tree *dt = nullptr;
-    check(vb_kdtree_import(context(), pre.data(), idx.data(), t.size, &dt), "vb_kdtree_import");
-    return tb.put(t.root, dt, t.size);
+    check(vb_kdtree_import(context(), pre.data(), idx.data(), n, &dt), "vb_kdtree_import");
+    return tb.put(t.root, dt, n);
 }
 
 // CSR radius query with retry on capacity

@@ -108,6 +108,7 @@ struct vb_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of vb_pairs_run
     vb_ctx *twin = nullptr;   // second stream + second set of workspaces: vb_pairs_run alternates sub-batches between the two
     std::vector<cudaEvent_t> events;                      // untimed events for the copy/compute pipeline
+    void *pairs_stream = nullptr;                         // vb_pairs_submit / vb_pairs_wait slots (stream.cu)
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];
     uint64_t launches = 0;
@@ -120,6 +121,8 @@ struct vb_ctx {
     void prof_begin(const char *name);
     void prof_end(const char *name);
 };
+
+namespace vb { void pairs_stream_release(vb_ctx *ctx); }
 
 struct vb_tree {
     vb_ctx *ctx = nullptr;

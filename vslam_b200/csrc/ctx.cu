@@ -61,6 +61,7 @@ int vb_destroy(vb_ctx *c) {
     }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    vb::pairs_stream_release(c);
     for (auto &b : c->ws) b.release();
     for (auto &b : c->pin) b.release();
     for (auto &kv : c->prof) {

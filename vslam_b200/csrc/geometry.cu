@@ -41,6 +41,20 @@ __global__ void __launch_bounds__(64) k_extract_rt(const float *__restrict__ F_a
 #pragma unroll
         for (int i = 0; i < 9; i++) E_all[(size_t)p * 9 + i] = E[i];
     svd3x3(E, U, D, Vt);                                            // :7
+    {   // exactly singular E: svd3x3 leaves a zero (sv == 0) or noise (sv < 2^-40 sv0) third column of U; complete the basis
+        // as cv::SVD's FULL_UV does
+        const double n2c = __dadd_rn(__dadd_rn(__dmul_rn((double)U[2], (double)U[2]), __dmul_rn((double)U[5], (double)U[5])),
+                                     __dmul_rn((double)U[8], (double)U[8]));
+        if (!(n2c >= 0.5) || !(D[2] > __fmul_rn(D[0], 9.094947017729282e-13f))) {
+            const double c0 = __dsub_rn(__dmul_rn((double)U[3], (double)U[7]), __dmul_rn((double)U[6], (double)U[4]));
+            const double c1 = __dsub_rn(__dmul_rn((double)U[6], (double)U[1]), __dmul_rn((double)U[0], (double)U[7]));
+            const double c2 = __dsub_rn(__dmul_rn((double)U[0], (double)U[4]), __dmul_rn((double)U[3], (double)U[1]));
+            const double ci = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(c0, c0), __dmul_rn(c1, c1)), __dmul_rn(c2, c2))));
+            U[2] = __double2float_rn(__dmul_rn(c0, ci));
+            U[5] = __double2float_rn(__dmul_rn(c1, ci));
+            U[8] = __double2float_rn(__dmul_rn(c2, ci));
+        }
+    }
     float t[3] = {U[2], U[5], U[8]};                                // :9
     const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)t[0], (double)t[0]), __dmul_rn((double)t[1], (double)t[1])),
                                 __dmul_rn((double)t[2], (double)t[2]));

@@ -1,20 +1,22 @@
 // pairs.cu — whole-pair pipeline: match_features (reference src/Frame.cpp:82-105) for one pair or for
 // every consecutive pair of a frame sequence, with all intermediates kept on the device.
 //
-// Per batch of P pairs the launch sequence is fixed (6 kernels, independent of P):
-//   k_knn2_partial -> k_knn2_finish (ratio test, ordered compaction, float4 correspondences, match count)
-//   -> k_sample_sets -> k_solve8 -> k_score -> k_select (best model, mask, inlier matches in order)
+// Per batch of P pairs the launch sequence is fixed (independent of P). Large 256-bit problems:
+//   k_expand_e2m1 -> k_knn2_tc4 (tcgen05 kNN candidates) -> k_knn2_tc_fix (exact XOR+POPC on the candidate group)
+//   -> k_knn2_finish (ratio test, ordered compaction, float4 correspondences, match count)
+//   -> k_sample_sets -> k_solve8 -> k_bq_init + k_count_queue (bounded inlier counting; k_corr_bounds + k_count2 for small
+//   batches) -> k_select (tie scores, best model, mask, inlier matches in order).
+// Small or non-256-bit problems replace the first three by k_knn2_partial (XOR + POPC tiles).
 // Pair i samples with std::mt19937(seed0 + i), i.e. what the reference would draw had
 // std::random_device returned seed0 + i for that frame.
 #include "common.cuh"
 #include "hamming_dev.cuh"
 #include "ransac_dev.cuh"
+#include "pairs_dev.cuh"
 
 namespace vb {
 
-constexpr uint32_t PAIRS_MAX_BATCH = 1024;
-
-static int pairs_core(vb_ctx *ctx, uint32_t P, const float2 *p1_base, const float2 *p2_base, size_t pts_stride,
+int pairs_core(vb_ctx *ctx, uint32_t P, const float2 *p1_base, const float2 *p2_base, size_t pts_stride,
                       const uint32_t *d1_base, const uint32_t *d2_base, size_t desc_stride_words, uint32_t n1, uint32_t n2,
                       uint32_t bytes, const vb_pair_params &prm, uint32_t seed0, vb_pair_result *results_d,
                       int2 *out_matches_d) {
@@ -42,7 +44,7 @@ static int pairs_core(vb_ctx *ctx, uint32_t P, const float2 *p1_base, const floa
                       ctx->ws[WS_TENT].as<int2>(), out_matches_d, true);
 }
 
-static int check_params(const vb_pair_params *p, uint32_t bytes, uint32_t n2) {
+int pairs_check_params(const vb_pair_params *p, uint32_t bytes, uint32_t n2) {
     VB_REQUIRE(p != nullptr, VB_ERR_INVALID, "params is NULL");
     VB_REQUIRE(p->min_items >= 1 && p->min_items <= 8, VB_ERR_INVALID, "min_items must be in 1..8");
     VB_REQUIRE(p->max_iterations > 0, VB_ERR_INVALID, "max_iterations is 0");
@@ -61,7 +63,7 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
                    const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d) {
     VB_REQUIRE(ctx && pts_d && desc_d && results_d, VB_ERR_INVALID, "NULL argument");
     int rc;
-    if ((rc = check_params(params, bytes, k))) return rc;
+    if ((rc = pairs_check_params(params, bytes, k))) return rc;
     if (nframes < 2) return VB_OK;
     VB_CUDA(cudaSetDevice(ctx->device));
     const uint32_t P = nframes - 1, W = bytes / 4;
@@ -121,7 +123,7 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
                  const vb_pair_params *params, vb_pair_result *results, int32_t *out_matches) {
     VB_REQUIRE(ctx && pts && desc && results, VB_ERR_INVALID, "NULL argument");
     int rc;
-    if ((rc = check_params(params, bytes, k))) return rc;
+    if ((rc = pairs_check_params(params, bytes, k))) return rc;
     if (nframes < 2) return VB_OK;
     VB_CUDA(cudaSetDevice(ctx->device));
     const uint32_t P = nframes - 1;
@@ -185,36 +187,50 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     uint8_t *desc_d = ctx->ws[WS_DESC].as<uint8_t>();
     vb_pair_result *res_d = ctx->ws[WS_RESULT].as<vb_pair_result>();
     int2 *outm_d = out_matches ? ctx->ws[WS_OUTMATCH].as<int2>() : nullptr;
-    // earlier work on the compute stream may still use these buffers
-    cudaEvent_t ev_prev = ctx->events[2 * nb];
-    VB_CUDA(cudaEventRecord(ev_prev, ctx->stream));
-    VB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_prev, 0));
-    for (uint32_t b = 0; b < nb; b++) {
-        const uint32_t f0 = b == 0 ? 0 : cut[b] + 1;   // first frame not yet uploaded
-        const uint32_t f1 = cut[b + 1] + 1;            // one past the halo frame
-        VB_CUDA(cudaMemcpyAsync(pts_d + (size_t)f0 * k * 2, pts + (size_t)f0 * k * 2, (size_t)(f1 - f0) * k * 8,
-                                cudaMemcpyHostToDevice, ctx->copy_in));
-        VB_CUDA(cudaMemcpyAsync(desc_d + (size_t)f0 * k * bytes, desc + (size_t)f0 * k * bytes, (size_t)(f1 - f0) * k * bytes,
-                                cudaMemcpyHostToDevice, ctx->copy_in));
-        VB_CUDA(cudaEventRecord(ctx->events[b], ctx->copy_in));
-    }
-    const float2 *pts2 = reinterpret_cast<const float2 *>(pts_d);
-    const uint32_t *desc32 = reinterpret_cast<const uint32_t *>(desc_d);
-    for (uint32_t b = 0; b < nb; b++) {
-        const uint32_t p0 = cut[b], pb = cut[b + 1] - cut[b];
-        vb_ctx *cx = (use_twin && ctx->twin && (b & 1)) ? ctx->twin : ctx;
-        VB_CUDA(cudaStreamWaitEvent(cx->stream, ctx->events[b], 0));
-        rc = pairs_core(cx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
-                        desc32 + (size_t)(p0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + p0,
-                        res_d + p0, outm_d ? outm_d + (size_t)p0 * k : nullptr);
-        if (rc) return rc;
-        VB_CUDA(cudaEventRecord(ctx->events[nb + b], cx->stream));
-        VB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->events[nb + b], 0));
-        VB_CUDA(cudaMemcpyAsync(results + p0, res_d + p0, (size_t)pb * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
-                                ctx->copy_out));
-        if (out_matches)
-            VB_CUDA(cudaMemcpyAsync(out_matches + (size_t)p0 * k * 2, outm_d + (size_t)p0 * k, (size_t)pb * k * 8,
-                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+    // Everything that enqueues work runs inside `enqueue`: if any step fails after the first asynchronous copy, the DMA
+    // engines may still be reading the caller's pts / desc or writing its results / out_matches, so every stream is
+    // drained before the error is returned (the caller is free to release those buffers as soon as this function returns).
+    auto enqueue = [&]() -> int {
+        // earlier work on the compute stream may still use these buffers
+        cudaEvent_t ev_prev = ctx->events[2 * nb];
+        VB_CUDA(cudaEventRecord(ev_prev, ctx->stream));
+        VB_CUDA(cudaStreamWaitEvent(ctx->copy_in, ev_prev, 0));
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t f0 = b == 0 ? 0 : cut[b] + 1;   // first frame not yet uploaded
+            const uint32_t f1 = cut[b + 1] + 1;            // one past the halo frame
+            VB_CUDA(cudaMemcpyAsync(pts_d + (size_t)f0 * k * 2, pts + (size_t)f0 * k * 2, (size_t)(f1 - f0) * k * 8,
+                                    cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaMemcpyAsync(desc_d + (size_t)f0 * k * bytes, desc + (size_t)f0 * k * bytes, (size_t)(f1 - f0) * k * bytes,
+                                    cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaEventRecord(ctx->events[b], ctx->copy_in));
+        }
+        const float2 *pts2 = reinterpret_cast<const float2 *>(pts_d);
+        const uint32_t *desc32 = reinterpret_cast<const uint32_t *>(desc_d);
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t p0 = cut[b], pb = cut[b + 1] - cut[b];
+            vb_ctx *cx = (use_twin && ctx->twin && (b & 1)) ? ctx->twin : ctx;
+            VB_CUDA(cudaStreamWaitEvent(cx->stream, ctx->events[b], 0));
+            rc = pairs_core(cx, pb, pts2 + (size_t)p0 * k, pts2 + (size_t)(p0 + 1) * k, k, desc32 + (size_t)p0 * k * W,
+                            desc32 + (size_t)(p0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + p0,
+                            res_d + p0, outm_d ? outm_d + (size_t)p0 * k : nullptr);
+            if (rc) return rc;
+            VB_CUDA(cudaEventRecord(ctx->events[nb + b], cx->stream));
+            VB_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->events[nb + b], 0));
+            VB_CUDA(cudaMemcpyAsync(results + p0, res_d + p0, (size_t)pb * sizeof(vb_pair_result), cudaMemcpyDeviceToHost,
+                                    ctx->copy_out));
+            if (out_matches)
+                VB_CUDA(cudaMemcpyAsync(out_matches + (size_t)p0 * k * 2, outm_d + (size_t)p0 * k, (size_t)pb * k * 8,
+                                        cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+    return VB_OK;
+    };
+    rc = enqueue();
+    if (rc != VB_OK) {
+        cudaStreamSynchronize(ctx->copy_in);
+        cudaStreamSynchronize(ctx->copy_out);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->twin) cudaStreamSynchronize(ctx->twin->stream);
+        return rc;
     }
     VB_CUDA(cudaStreamSynchronize(ctx->copy_out));
     VB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -230,7 +246,7 @@ int vb_match_features(vb_ctx *ctx, const float *p1, const uint8_t *d1, uint32_t 
                       uint32_t n2, uint32_t bytes, const vb_pair_params *params, int32_t *out_matches, vb_pair_result *result) {
     VB_REQUIRE(ctx && p1 && d1 && p2 && d2 && result, VB_ERR_INVALID, "NULL argument");
     int rc;
-    if ((rc = check_params(params, bytes, n2))) return rc;
+    if ((rc = pairs_check_params(params, bytes, n2))) return rc;
     VB_REQUIRE(n1 > 0, VB_ERR_TOO_FEW, "no query keypoints");
     VB_CUDA(cudaSetDevice(ctx->device));
     if ((rc = ctx->ws_ensure(WS_P1, (size_t)n1 * 8))) return rc;

@@ -43,7 +43,9 @@ EXPORTS = [
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
-    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms",
+    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
+    "vb_host_alloc", "vb_host_free", "vb_host_register", "vb_host_unregister",
+    "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms",
 ]
 
 
@@ -104,6 +106,20 @@ def load_library() -> C.CDLL:
     L.vb_match_features.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, C.POINTER(PairResult)]
     L.vb_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
+    L.vb_pairs_submit.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(C.c_int)]
+    L.vb_pairs_wait.argtypes = [vp, C.c_int, C.POINTER(u64)]
+    L.vb_pairs_run_compact.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(u64)]
+    L.vb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.vb_host_free.argtypes = [vp]
+    L.vb_host_register.argtypes = [vp, C.c_size_t]
+    L.vb_host_unregister.argtypes = [vp]
+    L.vb_multi_create.argtypes = [C.POINTER(C.c_int), u32, C.POINTER(vp)]
+    L.vb_multi_destroy.argtypes = [vp]
+    L.vb_multi_device_count.restype = u32
+    L.vb_multi_device_count.argtypes = [vp]
+    L.vb_multi_pairs_submit.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(C.c_int)]
+    L.vb_multi_pairs_wait.argtypes = [vp, C.c_int, C.POINTER(u64)]
+    L.vb_multi_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(u64)]
     L.vb_search_by_projection.argtypes = [vp, vp, vp, u32, vp, C.c_int, C.c_int, vp, u32, vp, vp, vp, f32, u32, vp, vp, vp,
                                           C.POINTER(u32)]
     L.vb_extract_rt.argtypes = [vp, vp, u32, vp, vp, vp, vp]
@@ -295,9 +311,92 @@ class Context:
         self._chk(self.L.vb_pairs_run(self.h, _ptr(pts), _ptr(desc), nframes, k, desc.shape[2], C.byref(prm), _ptr(res), _ptr(out)))
         return res[:nframes - 1], (out[:nframes - 1] if want_matches else None)
 
+    def pairs_submit(self, pts, desc, prm: PairParams, res, offsets, matches16):
+        """Asynchronous: the arrays must stay alive (and untouched) until pairs_wait(ticket)."""
+        nframes, k = pts.shape[0], pts.shape[1]
+        t = C.c_int(-1)
+        self._chk(self.L.vb_pairs_submit(self.h, _ptr(pts), _ptr(desc), nframes, k, desc.shape[2], C.byref(prm), _ptr(res),
+                                         _ptr(offsets), _ptr(matches16), 0 if matches16 is None else len(matches16), C.byref(t)))
+        return t.value
+
+    def pairs_wait(self, ticket):
+        tot = C.c_uint64(0)
+        self._chk(self.L.vb_pairs_wait(self.h, ticket, C.byref(tot)))
+        return tot.value
+
+    def pairs_run_compact(self, pts, desc, prm: PairParams, cap=None):
+        pts, desc = _f32(pts), np.ascontiguousarray(desc, np.uint8)
+        P, k = pts.shape[0] - 1, pts.shape[1]
+        res = np.zeros(max(P, 1), PAIR_RESULT_DTYPE)
+        off = np.zeros(max(P, 1), np.uint32)
+        m16 = np.zeros((max(P * k if cap is None else cap, 1), 2), np.uint16)
+        self.pairs_wait(self.pairs_submit(pts, desc, prm, res, off, m16))
+        return res[:P], off[:P], m16
+
+
+def pinned_empty(L, shape, dtype):
+    """numpy array over vb_host_alloc'd (pinned, portable) memory; keep the returned array alive, free with pinned_free."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = L.vb_host_alloc(max(n, 1), C.byref(p))
+    if rc != VB_OK:
+        raise VbError(rc, L.vb_last_error().decode())
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    return a, p
+
+
+def unpack_compact(res, offsets, matches16):
+    """[(n_i, 2) int32 arrays] from the compact download."""
+    return [matches16[int(o):int(o) + int(n)].astype(np.int32) for o, n in zip(offsets, res["n_matches"])]
+
+
+class Multi:
+    """vb_multi: one host thread + context per listed GPU inside this process."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.vb_multi_create(arr, len(devices), C.byref(h))
+        if rc != VB_OK:
+            raise VbError(rc, self.L.vb_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vb_multi_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc != VB_OK:
+            raise VbError(rc, self.L.vb_last_error().decode())
+
+    def submit(self, pts, desc, prm, res, offsets, matches16):
+        nframes, k = pts.shape[0], pts.shape[1]
+        t = C.c_int(-1)
+        self._chk(self.L.vb_multi_pairs_submit(self.h, _ptr(pts), _ptr(desc), nframes, k, desc.shape[2], C.byref(prm), _ptr(res),
+                                               _ptr(offsets), _ptr(matches16), 0 if matches16 is None else len(matches16),
+                                               C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        tot = C.c_uint64(0)
+        self._chk(self.L.vb_multi_pairs_wait(self.h, ticket, C.byref(tot)))
+        return tot.value
+
+    def pairs_run(self, pts, desc, prm):
+        pts, desc = _f32(pts), np.ascontiguousarray(desc, np.uint8)
+        P, k = pts.shape[0] - 1, pts.shape[1]
+        res = np.zeros(max(P, 1), PAIR_RESULT_DTYPE)
+        off, m16 = np.zeros(max(P, 1), np.uint32), np.zeros((max(P * k, 1), 2), np.uint16)
+        self.wait(self.submit(pts, desc, prm, res, off, m16))
+        return res[:P], off[:P], m16
+
 
 class KDTreeHandle:
-    def __init__(self, ctx: Context, handle, n):
+    def __init__(self, ctx: "Context", handle, n):
         self.ctx, self.h, self.n = ctx, handle, n
 
     def free(self):
