@@ -8,16 +8,22 @@ Workload (BASELINE.json configs[1]): every consecutive pair of a synthetic monoc
 ~205 MB (larger than the 126 MB L2), so consecutive steps do not find their inputs in L2.
 
   value  pairs/s, inputs resident in HBM (vb_pairs_run_d), CUDA events on the launching stream
-  e2e    pairs/s through the host-pointer C-ABI call (vb_pairs_run): pinned host buffers, H2D of all
-         frames and D2H of results + matches inside the timed region
-  roofline      the scoring kernel k_score (the north star's named kernel), logical 16 B per
-                (hypothesis, match) evaluation against the measured HBM peak; DESIGN.md explains why the
-                kernel is really FP32/FP64-issue bound
+  e2e    pairs/s through the host-pointer C-ABI (vb_pairs_submit / vb_pairs_wait, two submissions in flight): pinned
+         host buffers, H2D of every frame and D2H of results + compact matches inside the timed region, every step;
+         e2e.frac_of_copy_ceiling compares it with plain cudaMemcpyAsync traffic of the same byte counts on this box.
+         (e2e_blocking_call = the blocking vb_pairs_run, e2e_pageable = the same calls on pageable memory.)
+  roofline      the dominant kernel of the step, k_knn2_tc4 (tcgen05 kind::mxf4), against the fp4 tensor rate measured
+                on this GPU by vb_probe_tensor_peak (roofline.peak_measured_fp4); `counting` carries the RANSAC inlier
+                counting stage (the north star's named kernel) with SURVEY 8d's 16 logical bytes per evaluation
+  config3       BASELINE configs[2]: one pair, 20 000 keypoints, 128-d float descriptors, 4 096 hypotheses
+  config4       BASELINE configs[3]: ONE 10 001-frame sequence cut into contiguous pair ranges over the ranks (strong scaling)
+  score_sweep   BASELINE configs[4]: matches x hypotheses corners of the scoring entry point
   cpu_baseline  the C oracle (port of the reference path) on the box's host cores, bounded sample
   --impl reference   times that CPU path with all host threads instead of the GPU path
 
 N > 1 (torchrun): every rank owns its own sequence shard on its own GPU (weak scaling), no data-path
-collective; gloo is used only for the barrier and the max-over-ranks of the device time.
+collective; gloo is used only for the barrier and the max-over-ranks of the device time. e2e_multi is the same work
+driven by ONE process (rank 0) through vb_multi — one host thread + context per GPU, results landing in one host array.
 """
 import argparse
 import ctypes as C
@@ -51,7 +57,9 @@ def parse():
     ap.add_argument("--hyps", type=int, default=1024)
     ap.add_argument("--threshold", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also run the config-5 scoring sweep corner (1M x 16384)")
+    ap.add_argument("--sweep", action="store_true", help="(kept for compatibility: the config-5 corners are always run)")
+    ap.add_argument("--frames-total", type=int, default=10001, help="config 4: frames of the ONE sequence sharded over the ranks")
+    ap.add_argument("--quick", action="store_true", help="skip config3 / config4 / score_sweep / kd-tree extras")
     return ap.parse_args()
 
 
@@ -184,6 +192,40 @@ def workload_config(args, pairs_per_rank, device=True):
                   else "host run: bounded sample of the same sequence, %.0f MB of inputs per step" % mb}
 
 
+def copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, steps, barrier, max_over_ranks):
+    """Seconds per step (max over ranks) and GB/s per GPU of plain cudaMemcpyAsync traffic: h2d_bytes up and d2h_bytes down
+    per step from / to pinned memory on two streams at once, every rank simultaneously, no kernels."""
+    src_h = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    dst_d = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    src_d = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    dst_h = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(n):
+        for _ in range(n):
+            with torch.cuda.stream(s_up):
+                dst_d.copy_(src_h, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                dst_h.copy_(src_d, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+    run(2)
+    barrier()
+    t0 = time.perf_counter()
+    run(steps)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0) / steps
+    return dt, (h2d_bytes + d2h_bytes) / dt / 1e9
+
+
+def reflected_frames(first, count, period):
+    """Frame indices into a base sequence of period + 1 frames for frames [first, first + count) of a long sequence that
+    walks the base forwards, then backwards, then forwards ... (every consecutive pair is a genuine consecutive pair of
+    the base sequence, traversed in one direction or the other)."""
+    j = np.arange(first, first + count) % (2 * period)
+    return np.where(j <= period, j, 2 * period - j)
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -294,7 +336,8 @@ def main():
     P_prof = P - 1024 * ((P - 1) // 1024)
     tent_prof = int(res["n_tentative"][P - P_prof:].sum())
     # dominant kernel of the step: the tensor-core matcher
-    roofline = hamming_roofline(P_prof, k, ham_ms_avg, bf16_peak, peak_src)
+    probe = tensor_probe(ctx)
+    roofline = hamming_roofline(P_prof, k, ham_ms_avg, bf16_peak, peak_src, probe)
     if roofline is not None:
         roofline["traffic"] = ncu_traffic("k_knn2_tc4", P_prof, k, args.hyps)
         roofline["pairs_per_launch"] = P_prof
@@ -319,22 +362,87 @@ def main():
     # kernel_ms covers the last batch of P_prof pairs; its share of the step is scaled to the step's P pairs
     shares = {n: (v * (P / P_prof) / step_ms if v and v > 0 else None) for n, v in kt.items()}
 
-    # ---- end to end through the host-pointer ABI call -------------------------------------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
+    # ---- end to end through the host-pointer C ABI ---------------------------------------------------------------
+    # Streaming submission: two tickets in flight, so the upload of step i+1 and the download of step i-1 overlap the kernels
+    # of step i. Every step uploads all of its frames from pinned host memory and downloads every pair's result + matches.
+    e_steps = max(20, args.steps)
+    outs = [(torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+             torch.zeros(P, dtype=torch.int32).pin_memory(),
+             torch.zeros((P * k, 2), dtype=torch.int16).pin_memory()) for _ in range(2)]
+
+    def submit(i, pp, dd, oo):
+        t = C.c_int(-1)
+        r_, o_, m_ = oo[i & 1]
+        ctx._chk(ctx.L.vb_pairs_submit(ctx.h, pp, dd, nframes, k, nbytes, C.byref(prm), r_.data_ptr(), o_.data_ptr(),
+                                       m_.data_ptr(), P * k, C.byref(t)))
+        return t.value
+
+    def stream_steps(n, pp, dd, oo):
+        """n pipelined steps; returns the match count of the last one."""
+        tk = submit(0, pp, dd, oo)
+        tot = C.c_uint64(0)
+        for i in range(1, n):
+            tn = submit(i, pp, dd, oo)
+            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, C.byref(tot)))
+            tk = tn
+        ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, C.byref(tot)))
+        return int(tot.value)
+
+    stream_steps(max(3, args.warmup), pts_h.data_ptr(), desc_h.data_ptr(), outs)
     barrier()
     t0 = time.perf_counter()
-    e_steps = max(1, min(args.steps, 3))
-    for _ in range(e_steps):
-        step_e2e()
+    total_matches = stream_steps(e_steps, pts_h.data_ptr(), desc_h.data_ptr(), outs)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()   # sampled every 20 ms across both timed regions (device-resident and end-to-end)
-    res_e = res_h.numpy().view(PAIR_RESULT_DTYPE)
+    last = outs[(e_steps - 1) & 1]
+    res_e = last[0].numpy().view(PAIR_RESULT_DTYPE)
+    off_e = last[1].numpy().view(np.uint32)
+    m16_e = last[2].numpy().view(np.uint16)
     assert np.array_equal(res_e["n_matches"], res["n_matches"]), "e2e and device-resident paths disagree"
-    e2e = {"value": world * P * e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(pts_h.numel() * 4 + desc_h.numel()),
-           "d2h_bytes_per_step": int(res_h.numel() + out_h.numel() * 4), "steps": e_steps}
+    h2d_bytes = int(pts_h.numel() * 4 + desc_h.numel())
+    d2h_bytes = int(P * PAIR_RESULT_DTYPE.itemsize + P * 4 + total_matches * 4)
+    e2e = {"value": world * P * e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": d2h_bytes, "steps": e_steps,
+           "api": "vb_pairs_submit / vb_pairs_wait, 2 submissions in flight, pinned host buffers, compact uint16 matches",
+           "frac_of_device_resident": (world * P * e_steps / e2e_s) / value}
+    # the ceiling of this box for the same traffic: plain cudaMemcpyAsync H2D + D2H of the same byte counts, both
+    # directions at once, every rank at the same time, nothing computing
+    ceil_s, ceil_gbs = copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, 10, barrier, max_over_ranks)
+    e2e["copy_ceiling_pairs_per_s"] = world * P / ceil_s
+    e2e["copy_ceiling_GBps_per_gpu"] = ceil_gbs
+    e2e["frac_of_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling_pairs_per_s"]
+    e2e["bound"] = "compute (device-resident step time)" if e2e["copy_ceiling_pairs_per_s"] > value else "host copies"
+
+    # the blocking call (vb_pairs_run: int32 [pairs][k][2] match slab) and the streaming calls on PAGEABLE memory
+    def step_blocking():
+        ctx._chk(ctx.L.vb_pairs_run(ctx.h, pts_h.data_ptr(), desc_h.data_ptr(), nframes, k, nbytes, C.byref(prm),
+                                    res_h.data_ptr(), out_h.data_ptr()))
+    step_blocking()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step_blocking()
+    barrier()
+    blocking_s = max_over_ranks(time.perf_counter() - t0)
+    out_e = out_h.numpy()
+    pouts = [(np.zeros(P, PAIR_RESULT_DTYPE), np.zeros(P, np.uint32), np.zeros((P * k, 2), np.uint16)) for _ in range(2)]
+
+    class _NP:   # pageable numpy buffers behind the same .data_ptr() interface
+        def __init__(self, a): self.a = a
+        def data_ptr(self): return self.a.ctypes.data
+    pouts_w = [tuple(_NP(a) for a in o) for o in pouts]
+    stream_steps(2, pts.ctypes.data, desc.ctypes.data, pouts_w)
+    barrier()
+    t0 = time.perf_counter()
+    stream_steps(5, pts.ctypes.data, desc.ctypes.data, pouts_w)
+    barrier()
+    pageable_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.array_equal(pouts[0][0]["n_matches"], res["n_matches"])
+    e2e_other = {"e2e_blocking_call": {"value": world * P * 5 / blocking_s, "unit": UNIT, "api": "vb_pairs_run (blocking, int32 slab)",
+                                       "d2h_bytes_per_step": int(res_h.numel() + out_h.numel() * 4), "steps": 5},
+                 "e2e_pageable": {"value": world * P * 5 / pageable_s, "unit": UNIT, "steps": 5,
+                                  "api": "vb_pairs_submit / vb_pairs_wait on pageable (malloc) host memory"}}
 
     # ---- single-pair latency through the reference-shaped call (match_features) ------------------
     fp0 = (pts[0], desc[0], pts[1], desc[1])
@@ -364,6 +472,7 @@ def main():
             same = (o["n"] == int(res["n_matches"][i]) == int(res_e["n_matches"][i]) and o["best"] == int(res["best_hyp"][i])
                     and o["n_tentative"] == int(res["n_tentative"][i])
                     and np.array_equal(out_e[i, :max(o["n"], 0)], o["matches"])
+                    and np.array_equal(m16_e[int(off_e[i]):int(off_e[i]) + max(o["n"], 0)].astype(np.int32), o["matches"])
                     and np.array_equal(np.ascontiguousarray(res["F"][i], np.float32).view(np.uint32).reshape(-1),
                                        np.ascontiguousarray(o["F"], np.float32).view(np.uint32).reshape(-1)))
             n_same += int(bool(same))
@@ -373,6 +482,17 @@ def main():
                "sample": f"{sample} pairs over {used} OpenMP threads in {dtN:.1f} s (oracle C port, -O3 -march=native)",
                "single_thread_pairs_per_s": v1, "host_cpus": cores, "gpu_matches_oracle_on_pair0": parity,
                "gpu_matches_oracle_on_sampled_pairs": "%d of %d" % (n_same, len(sample_pairs))}
+
+    # ---- BASELINE configs[3]: ONE long sequence cut over the ranks (strong scaling), every rank takes part --------------
+    config4 = None if args.quick else config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, barrier,
+                                                     max_over_ranks)
+    # ---- the same weak-scaling work driven by ONE process through vb_multi (rank 0; the other ranks idle at the barrier)
+    e2e_multi = None
+    if world > 1 and not args.quick:
+        barrier()
+        if rank == 0:
+            e2e_multi = multi_stage(args, torch, pts, desc, prm, world, P, k, nbytes)
+        barrier()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -387,10 +507,17 @@ def main():
                 "single_pair_match_features_ms": single_ms,
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
-        line["kdtree"] = kdtree_stage(ctx, torch, dev, pts, k)
-        line["search_by_projection"] = projection_stage(ctx, k, None if args.no_cpu_baseline else cpu_oracle())
-        if args.sweep:
+        line.update(e2e_other)
+        line["tensor_probe"] = probe
+        if config4 is not None:
+            line["config4"] = config4
+        if e2e_multi is not None:
+            line["e2e_multi"] = e2e_multi
+        if not args.quick:
+            line["config3"] = config3_stage(ctx, torch, dev, None if args.no_cpu_baseline else cpu_oracle())
             line["score_sweep"] = score_sweep(ctx, torch, dev, peak)
+            line["kdtree"] = kdtree_stage(ctx, torch, dev, pts, k)
+            line["search_by_projection"] = projection_stage(ctx, k, None if args.no_cpu_baseline else cpu_oracle())
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -398,22 +525,220 @@ def main():
     ctx.close()
 
 
-def hamming_roofline(P, k, ms, bf16_peak, peak_src):
+def hamming_roofline(P, k, ms, bf16_peak, peak_src, probe):
     """Dominant kernel of the step: k_knn2_tc4, tensor-pipe work. Algorithmic work = 2 * 256 flop per descriptor pair
-    (256-term +-1 dot product). The pipe it runs on is the fp4 one (kind::mxf4, K = 64 per UMMA): peak = 4 x the measured
-    dense bf16 figure (K = 16 per UMMA on the same pipe)."""
+    (256-term +-1 dot product). The peak it is divided by is MEASURED on this GPU in this run: back-to-back
+    tcgen05.mma kind::mxf4 (the kernel's own instruction shape, M128 N240 K64) from one thread per SM with resident
+    operands and no epilogue (vb_probe_tensor_peak). MEASURED_PEAKS.json has no fp4 entry; its bf16 figure and the
+    probe's own bf16 reading are printed next to it so the method can be judged."""
     if not ms or ms <= 0:
         return None
     fp4 = os.environ.get("VB_HAMMING_FP4", "1") != "0"
-    mult = 4.0 if fp4 else 2.0
     tf = 2.0 * 256.0 * float(P) * k * k / (ms * 1e-3) / 1e12
+    peak = probe["mxf4_n240"] if fp4 else probe["f8f6f4_n256"]
     return {"kernel": "k_knn2_tc4 (tcgen05 kind::mxf4, e2m1 +-1, ue8m0 2^7 scales)" if fp4 else
                       "k_knn2_tc (tcgen05 kind::f8f6f4, e4m3 +-128)",
-            "bound": "tensor", "achieved": tf, "peak": mult * bf16_peak, "unit": "TFLOP/s", "frac": tf / (mult * bf16_peak),
-            "peak_source": peak_src + (", fp4 = 4 x bf16" if fp4 else ", fp8 = 2 x bf16"),
+            "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "peak_source": "measured in this run: vb_probe_tensor_peak, UMMA-only loop of the kernel's instruction shape "
+                           "(no MEASURED_PEAKS.json entry exists for fp4)",
+            "peak_measured_fp4": probe["mxf4_n256"], "peak_measured_fp4_n240": probe["mxf4_n240"],
+            "peak_measured_fp8": probe["f8f6f4_n256"], "peak_measured_bf16_probe": probe["bf16_n256"],
+            "peak_bf16_measured_peaks_json": bf16_peak, "peak_bf16_source": peak_src,
+            "frac_of_4x_bf16_measured_peaks": tf / (4.0 * bf16_peak), "frac_of_nominal_9000": tf / 9000.0,
             "ms_per_launch": ms, "pair_distances_per_s": float(P) * k * k / (ms * 1e-3),
-            "note": "the drain (max tree + top-2 bookkeeping on the ALU pipe, 66 % busy) shares the limit with the tensor pipe "
-                    "(60-69 % active under ncu); the MMA-only floor of this kernel is 1.9 us per 5k x 5k pair, measured 2.6"}
+            "padding": "tiles are 256 queries x 240 train rows: 5120 x 5040 evaluated for 5000 x 5000 (3.2 % of the MMA work)"}
+
+
+def tensor_probe(ctx):
+    """UMMA-only rates (TFLOP/s) on this GPU: the matcher's fp4 shape, the square fp4 / fp8 shapes, and bf16 as a cross-check
+    of the method against the cuBLAS figure in MEASURED_PEAKS.json."""
+    return {"mxf4_n240": ctx.probe_tensor_peak(0, 240), "mxf4_n256": ctx.probe_tensor_peak(0, 256),
+            "f8f6f4_n256": ctx.probe_tensor_peak(1, 256, iters=2048), "bf16_n256": ctx.probe_tensor_peak(2, 256, iters=1024),
+            "how": "k_probe_umma: 1 CTA per SM, one thread issues 4 K-steps x iters tcgen05.mma (M128) on shared-memory "
+                   "resident operands into one TMEM accumulator, best of 5 launches, CUDA events"}
+
+
+def config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, barrier, max_over_ranks):
+    """BASELINE configs[3] as written: ONE synthetic sequence of --frames-total frames (10 001: 10 000 pairs), its pairs cut
+    into contiguous ranges over the ranks, each range with a one-frame halo (strong scaling: total work fixed). The long
+    sequence walks this run's 1 025-frame base sequence forwards and backwards (every pair is a genuine consecutive pair);
+    pair i samples with seed0 + i whatever rank it lands on. Device-resident time by CUDA events, end to end through
+    vb_pairs_submit / vb_pairs_wait in 1 024-pair chunks from pinned memory; max over ranks."""
+    from vslam_b200.lib import PAIR_RESULT_DTYPE
+    from vslam_b200.sequence import shard_pairs
+    total_pairs = args.frames_total - 1
+    k, nbytes = pts.shape[1], desc.shape[2]
+    from vslam_b200 import synth
+    base_p, base_d = (pts, desc) if rank == 0 else synth.sequence(pts.shape[0], k, 1000)   # every rank: rank 0's base
+    b, e = shard_pairs(total_pairs, world)[rank]
+    np_r = e - b
+    fidx = reflected_frames(b, np_r + 1, pts.shape[0] - 1)
+    sp = torch.from_numpy(np.ascontiguousarray(base_p[fidx])).pin_memory()
+    sd = torch.from_numpy(np.ascontiguousarray(base_d[fidx])).pin_memory()
+    sp_d, sd_d = sp.to(dev), sd.to(dev)
+    res_d = torch.zeros(max(np_r, 1) * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    out_d = torch.zeros((max(np_r, 1), k, 2), dtype=torch.int32, device=dev)
+    prm4 = ctx.params(0.7, 8, args.hyps, args.threshold, 1 + b)
+
+    def dev_pass():
+        ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, sp_d.data_ptr(), sd_d.data_ptr(), np_r + 1, k, nbytes, C.byref(prm4),
+                                      res_d.data_ptr(), out_d.data_ptr()))
+    dev_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(stream)
+    for _ in range(reps):
+        dev_pass()
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    r4 = res_d.cpu().numpy().view(PAIR_RESULT_DTYPE)[:np_r]
+    # end to end: 1 024-pair chunks (one-frame halo each), two in flight
+    CH = 1024
+    chunks = [(c, min(c + CH, np_r)) for c in range(0, np_r, CH)]
+    res_h = torch.zeros(max(np_r, 1) * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    off_h = torch.zeros(max(np_r, 1), dtype=torch.int32).pin_memory()
+    m16_h = torch.zeros((max(np_r, 1) * k, 2), dtype=torch.int16).pin_memory()
+
+    def e2e_pass():
+        tickets, tot = [], C.c_uint64(0)
+        for ci, (c0, c1) in enumerate(chunks):
+            t = C.c_int(-1)
+            pc = ctx.params(0.7, 8, args.hyps, args.threshold, 1 + b + c0)
+            ctx._chk(ctx.L.vb_pairs_submit(ctx.h, sp.data_ptr() + c0 * k * 8, sd.data_ptr() + c0 * k * nbytes, c1 - c0 + 1, k, nbytes,
+                                           C.byref(pc), res_h.data_ptr() + c0 * PAIR_RESULT_DTYPE.itemsize,
+                                           off_h.data_ptr() + c0 * 4, m16_h.data_ptr() + c0 * k * 4, (c1 - c0) * k, C.byref(t)))
+            tickets.append(t.value)
+            if len(tickets) == 2:
+                ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tickets.pop(0), C.byref(tot)))
+        for t in tickets:
+            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, t, C.byref(tot)))
+    e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_pass()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / reps
+    rh = res_h.numpy().view(PAIR_RESULT_DTYPE)[:np_r]
+    same = bool(np.array_equal(rh["n_matches"], r4["n_matches"]) and np.array_equal(rh["best_hyp"], r4["best_hyp"]))
+    ok = int((r4["status"] == 0).sum())
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ok, int(same)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ok, same = int(t[0]), bool(int(t[1]) == world)
+    return {"workload": "BASELINE configs[3]: one %d-frame sequence, %d kpts/frame, pairs sharded over %d GPU(s) in contiguous "
+                        "ranges with a one-frame halo" % (args.frames_total, k, world),
+            "scaling": "strong", "pairs_total": total_pairs, "pairs_this_rank": np_r, "n_gpus": world,
+            "device_resident": {"value": total_pairs / (dev_ms * 1e-3), "unit": UNIT, "ms_per_pass": dev_ms},
+            "e2e": {"value": total_pairs / e2e_s, "unit": UNIT, "ms_per_pass": e2e_s * 1e3,
+                    "h2d_bytes_per_pass_per_rank": int(sp.numel() * 4 + sd.numel()), "chunk_pairs": CH},
+            "pairs_with_model": ok, "e2e_equals_device_resident": same, "passes": reps}
+
+
+def multi_stage(args, torch, pts, desc, prm, world, P, k, nbytes):
+    """The weak-scaling workload (world x P pairs) driven by ONE process through vb_multi: one host thread + context + streams
+    per GPU, every GPU's results landing in one host array (the host gather). Two submissions in flight."""
+    from vslam_b200.lib import PAIR_RESULT_DTYPE, Multi
+    tp = world * P
+    fidx = reflected_frames(0, tp + 1, pts.shape[0] - 1)
+    ph = torch.from_numpy(np.ascontiguousarray(pts[fidx])).pin_memory()
+    dh = torch.from_numpy(np.ascontiguousarray(desc[fidx])).pin_memory()
+    outs = [(torch.zeros(tp * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+             torch.zeros(tp, dtype=torch.int32).pin_memory(),
+             torch.zeros((tp * k, 2), dtype=torch.int16).pin_memory()) for _ in range(2)]
+    m = Multi(list(range(world)))
+    try:
+        def submit(i):
+            t = C.c_int(-1)
+            r_, o_, m_ = outs[i & 1]
+            m._chk(m.L.vb_multi_pairs_submit(m.h, ph.data_ptr(), dh.data_ptr(), tp + 1, k, nbytes, C.byref(prm), r_.data_ptr(),
+                                             o_.data_ptr(), m_.data_ptr(), tp * k, C.byref(t)))
+            return t.value
+
+        def steps(n):
+            tk, tot = submit(0), C.c_uint64(0)
+            for i in range(1, n):
+                tn = submit(i)
+                m._chk(m.L.vb_multi_pairs_wait(m.h, tk, C.byref(tot)))
+                tk = tn
+            m._chk(m.L.vb_multi_pairs_wait(m.h, tk, C.byref(tot)))
+            return int(tot.value)
+        steps(3)
+        n = max(10, min(args.steps, 20))
+        t0 = time.perf_counter()
+        tot = steps(n)
+        dt = time.perf_counter() - t0
+        r = outs[(n - 1) & 1][0].numpy().view(PAIR_RESULT_DTYPE)
+        return {"value": tp * n / dt, "unit": UNIT, "steps": n, "pairs_per_step": tp, "n_gpus": world,
+                "api": "vb_multi_pairs_submit / vb_multi_pairs_wait: 1 process, %d host threads, results gathered in one host array" % world,
+                "h2d_bytes_per_step": int(ph.numel() * 4 + dh.numel()), "d2h_bytes_per_step": int(tp * 64 + tot * 4),
+                "pairs_with_model": int((r["status"] == 0).sum())}
+    finally:
+        m.close()
+
+
+def config3_stage(ctx, torch, dev, orc):
+    """BASELINE configs[2]: one pair, 20 000 keypoints, 128-d float descriptors, 4 096 hypotheses — match_features in one call
+    (tcgen05 bf16 candidate GEMM + exact fp32 re-evaluation, ratio test, RansacFilter, inlier copy-out)."""
+    from vslam_b200 import synth
+    from vslam_b200.lib import PAIR_RESULT_DTYPE
+    n, dim, H = 20000, 128, 4096
+    fp = synth.frame_pair_float(n, 5, dim=dim)
+    prm = ctx.params(0.7, 8, H, 10.0, 77)
+    t = {x: torch.from_numpy(fp[x]).to(dev) for x in ("p1", "d1", "p2", "d2")}
+    res_d = torch.zeros(PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    out_d = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+    call = lambda: ctx._chk(ctx.L.vb_match_features_l2f_d(ctx.h, t["p1"].data_ptr(), t["d1"].data_ptr(), n, t["p2"].data_ptr(),
+                                                          t["d2"].data_ptr(), n, dim, C.byref(prm), out_d.data_ptr(), res_d.data_ptr()))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream(dev)
+    reps = 10
+    e0.record(st)
+    for _ in range(reps):
+        call()
+    e1.record(st)
+    torch.cuda.synchronize(dev)
+    dev_ms = e0.elapsed_time(e1) / reps
+    ctx.profile(True)
+    call()
+    torch.cuda.synchronize(dev)
+    kms = {nm: ctx.profile_ms(nm) for nm in ("l2f", "l2f_gemm", "l2f_rerank", "finish", "sample", "solve", "score", "select")}
+    ctx.profile(False)
+    g = ctx.match_features_l2f(fp["p1"], fp["d1"], fp["p2"], fp["d2"], prm)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        g = ctx.match_features_l2f(fp["p1"], fp["d1"], fp["p2"], fp["d2"], prm)
+    host_ms = (time.perf_counter() - t0) / 5 * 1e3
+    r = res_d.cpu().numpy().view(PAIR_RESULT_DTYPE)[0]
+    out = {"workload": "BASELINE configs[2]: 1 pair, 20000 kpts, 128-d float descriptors, 4096 hypotheses, threshold 10",
+           "device_resident_ms": dev_ms, "pairs_per_s_device_resident": 1e3 / dev_ms, "host_call_ms": host_ms,
+           "pairs_per_s_host_call": 1e3 / host_ms, "kernel_ms": {a: b for a, b in kms.items() if b and b > 0},
+           "gemm_TFLOPs": (2.0 * n * n * dim / (kms["l2f_gemm"] * 1e-3) / 1e12) if kms.get("l2f_gemm", -1) > 0 else None,
+           "n_tentative": int(r["n_tentative"]), "n_matches": int(r["n_matches"]), "best_hyp": int(r["best_hyp"]),
+           "host_call_equals_device": bool(g["n"] == int(r["n_matches"]) and g["best"] == int(r["best_hyp"]))}
+    if orc is not None:
+        # parity on a bounded sample: the oracle's kNN-2 + ratio on 256 queries against the full train set, and the oracle's
+        # find_fundamental on the GPU's tentative list
+        qs = np.arange(0, n, n // 256)[:256]
+        oi, od = orc.knn2_l2f(np.ascontiguousarray(fp["d1"][qs]), fp["d2"])
+        gi, gd = ctx.knn2_l2f(fp["d1"], fp["d2"])
+        knn_same = bool(np.array_equal(gi[qs], oi) and np.array_equal(gd[qs].view(np.uint32), od.view(np.uint32)))
+        tent = ctx.match_l2f(fp["d1"], fp["d2"], 0.7)
+        t0 = time.perf_counter()
+        o = orc.find_fundamental(fp["p1"], fp["p2"], tent, 8, H, 10.0, 77)
+        cpu_ransac_ms = (time.perf_counter() - t0) * 1e3
+        out["oracle_check"] = {"knn2_on_256_queries": knn_same,
+                               "find_fundamental": bool(o["best"] == g["best"] and o["n_inliers"] == g["n_inliers"]
+                                                        and np.array_equal(tent[o["mask"].astype(bool)], g["matches"])
+                                                        and np.array_equal(o["F"].view(np.uint32), g["F"].view(np.uint32))),
+                               "cpu_oracle_find_fundamental_ms_1core": cpu_ransac_ms}
+    return out
 
 
 def kdtree_stage(ctx, torch, dev, pts, k):
@@ -509,21 +834,24 @@ def projection_stage(ctx, k, orc):
 
 
 def score_sweep(ctx, torch, dev, peak):
-    """BASELINE config 5 corners: matches x hypotheses, device-resident, CUDA events."""
+    """BASELINE configs[4] corners: matches x hypotheses through vb_ransac_score_d (every hypothesis' inlier count AND residual
+    sum, the reference's compute_fundamental_residual :105-140), device-resident, CUDA events inside the library: the scoring
+    kernel alone and kernel + fold. logical_GBps = SURVEY 8d's 16 B per (hypothesis, match) evaluation / time."""
     from oracle_lib import Oracle
     from vslam_b200 import synth
     orc = Oracle()
     out = []
     rng = np.random.default_rng(0)
     base = synth.correspondences(4000, 3)
-    for m, h in ((1000, 256), (16384, 1024), (262144, 4096), (1000000, 16384)):
-        corr = synth.correspondences(m, 11)
-        Fs = np.zeros((h, 9), np.float32)
-        nb = min(h, 512)
-        for i in range(nb):
-            sel = rng.choice(len(base), 8, replace=False)
-            Fs[i] = orc.compute_fundamental(base[sel, :2], base[sel, 2:]).reshape(-1)
-        Fs[nb:] = Fs[rng.integers(0, nb, h - nb)]
+    bank = np.zeros((512, 9), np.float32)
+    for i in range(len(bank)):
+        sel = rng.choice(len(base), 8, replace=False)
+        bank[i] = orc.compute_fundamental(base[sel, :2], base[sel, 2:]).reshape(-1)
+    corr_all = synth.correspondences(1000000, 11)
+    for m, h in ((1000, 256), (16384, 1024), (1000000, 256), (1000000, 1024), (262144, 4096), (1000000, 16384)):
+        corr = np.ascontiguousarray(corr_all[:m])
+        Fs = bank[rng.integers(0, len(bank), h)] if h > len(bank) else bank[:h]
+        Fs = np.ascontiguousarray(Fs)
         cd, fd = torch.from_numpy(corr).to(dev), torch.from_numpy(Fs).to(dev)
         cnt = torch.zeros(h, dtype=torch.int32, device=dev)
         sc = torch.zeros(h, dtype=torch.float32, device=dev)
@@ -531,17 +859,30 @@ def score_sweep(ctx, torch, dev, peak):
         for _ in range(3):
             call()
         torch.cuda.synchronize(dev)
-        ms = []
+        ms, ms_sel = [], []
         for _ in range(5):
             ctx.profile(True)
             call()
             torch.cuda.synchronize(dev)
             ms.append(ctx.profile_ms("score"))
+            ms_sel.append(ctx.profile_ms("select"))
             ctx.profile(False)
         t = float(np.mean(ms)) * 1e-3
+        tf = t + float(np.mean(ms_sel)) * 1e-3
         gbs = 16.0 * m * h / t / 1e9
-        out.append({"matches": m, "hypotheses": h, "ms": t * 1e3, "hyp_per_s": h / t, "evals_per_s": m * h / t,
-                    "logical_GBps": gbs, "frac_of_hbm_peak": gbs / peak})
+        row = {"matches": m, "hypotheses": h, "score_kernel_ms": t * 1e3, "score_plus_fold_ms": tf * 1e3, "hyp_per_s": h / tf,
+               "evals_per_s": m * h / tf, "logical_GBps": gbs, "logical_GBps_with_fold": 16.0 * m * h / tf / 1e9,
+               "frac_of_hbm_peak": gbs / peak}
+        # oracle check of three hypotheses (bounded: 3 x m residuals on one core)
+        p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+        mm = np.stack([np.arange(m), np.arange(m)], 1).astype(np.int32)
+        gc, gs_ = cnt.cpu().numpy(), sc.cpu().numpy()
+        okk = True
+        for hh in (0, h // 2, h - 1):
+            _, _, n_o, s_o = orc.residual(p1, p2, mm, Fs[hh].reshape(3, 3), 10.0)
+            okk = okk and int(gc[hh]) == n_o and np.float32(s_o).view(np.uint32) == gs_[hh:hh + 1].view(np.uint32)[0]
+        row["matches_oracle_on_3_hypotheses"] = bool(okk)
+        out.append(row)
     return out
 
 

@@ -192,6 +192,17 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
                  const vb_pair_params *params, vb_pair_result *results, int32_t *out_matches);
 int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint32_t nframes, uint32_t k,
                    uint32_t bytes, const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d);
+/* match_features with FLOAT descriptors (BASELINE config 3; the reference matcher is Hamming-only, src/Frame.cpp:83, so the
+ * matcher's contract is vb_knn2_l2f's and everything downstream — ratio test :91, find_fundamental :97, inlier copy-out
+ * :98-102 — is the reference's): d1 [n1][dim], d2 [n2][dim] fp32, dim 64 or 128. One call, nothing returns to the host
+ * between the matcher and the inlier list. The _d variant takes device pointers, writes result_d[0] / out_matches_d[n1][2]
+ * on the device and only enqueues. */
+int vb_match_features_l2f(vb_ctx *ctx, const float *p1_xy, const float *d1, uint32_t n1, const float *p2_xy, const float *d2,
+                          uint32_t n2, uint32_t dim, const vb_pair_params *params, int32_t *out_matches,
+                          vb_pair_result *result);
+int vb_match_features_l2f_d(vb_ctx *ctx, const float *p1_xy_d, const float *d1_d, uint32_t n1, const float *p2_xy_d,
+                            const float *d2_d, uint32_t n2, uint32_t dim, const vb_pair_params *params,
+                            int32_t *out_matches_d, vb_pair_result *result_d);
 
 /* ------------------------------------------------------------------------------------------------
  * Streaming submission with a compact result download — for callers that process one sequence after another (the
@@ -280,6 +291,13 @@ int vb_triangulate(vb_ctx *ctx, const float *p1, const float *p2, uint32_t n, co
  * stream during the last call, keyed by name ("score", "hamming", "solve", ...). Returns <0 if unknown.
  * ---------------------------------------------------------------------------------------------- */
 int vb_profile_enable(vb_ctx *ctx, int on);
+/* Measurement hook (not on the product path): the rate at which this GPU retires back-to-back tcgen05.mma instructions of
+ * one kind from one issuing thread per SM — operands resident in shared memory, accumulator in TMEM, no loads, no epilogue.
+ * kind 0 = kind::mxf4.block_scale (e2m1, K = 64: the Hamming matcher's instruction), 1 = kind::f8f6f4 (e4m3, K = 32),
+ * 2 = kind::f16 (bf16, K = 16); M = 128, N = n_cols. Launches reps + 1 times, reports the fastest timed launch (CUDA events
+ * on the context's stream) and the flop count of one launch; bench.py prints flop / ms as roofline.peak_measured_*. */
+int vb_probe_tensor_peak(vb_ctx *ctx, int kind, uint32_t n_cols, uint32_t iters, uint32_t reps, float *best_ms,
+                         double *flop_per_launch);
 float vb_profile_last_ms(vb_ctx *ctx, const char *kernel_class);
 
 #ifdef __cplusplus

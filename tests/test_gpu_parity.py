@@ -510,6 +510,21 @@ def test_knn2_l2f_tensor_path_equals_exact_kernel_at_size(ctx, oracle, monkeypat
     assert np.array_equal(it[:200], oi) and np.array_equal(bits(dt[:200]), bits(od))
 
 
+@pytest.mark.parametrize("k,iters,seed", [(600, 64, 1), (3000, 256, 2), (6000, 512, 3)])
+def test_match_features_l2f_whole_pair(ctx, oracle, k, iters, seed):
+    """Float-descriptor match_features in ONE call (matcher -> ratio -> find_fundamental -> inlier copy-out on the device)
+    == oracle matcher + oracle find_fundamental (src/Frame.cpp:91-102, src/RansacFilter.cpp:36-67), bit for bit."""
+    fp = synth.frame_pair_float(k, seed)
+    prm = ctx.params(0.7, 8, iters, 10.0, 900 + seed)
+    g = ctx.match_features_l2f(fp["p1"], fp["d1"], fp["p2"], fp["d2"], prm)
+    tent = oracle.match_l2f(fp["d1"], fp["d2"], 0.7)
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 8, iters, 10.0, 900 + seed)
+    assert g["status"] == 0 and g["n_tentative"] == len(tent) and g["best"] == o["best"]
+    assert g["n_inliers"] == o["n_inliers"] and np.array_equal(bits(g["F"]), bits(o["F"]))
+    assert np.array_equal(g["matches"], tent[o["mask"].astype(bool)])
+    assert g["n"] > 0.3 * k
+
+
 # ---------------------------------------------------------------- counting kernel (the pair pipeline's scorer)
 @pytest.mark.parametrize("m,H,thr", [(1, 3, 10.0), (129, 70, 10.0), (3500, 1024, 10.0), (3500, 300, 0.2), (20000, 257, 10.0),
                                      (8193, 64, 1e-6), (3000, 64, 1e6)])
@@ -655,3 +670,56 @@ print("fallback kernels ok")
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "fallback kernels ok" in r.stdout, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- BASELINE configs 3 and 5 at full size
+def test_config3_full_size(ctx, oracle, monkeypatch):
+    """BASELINE configs[2] as stated: 20 000 x 20 000 x 128-d float descriptors, 4 096 hypotheses. The tensor-core matcher
+    equals the exact SIMT kernel on every query (indices and distance bits) and the oracle on a 400-query sample; the
+    one-call whole pair equals oracle find_fundamental on that tentative list (src/Frame.cpp:83-102, src/RansacFilter.cpp:36-67)."""
+    n, H = 20000, 4096
+    fp = synth.frame_pair_float(n, 5)
+    monkeypatch.setenv("VB_L2_TC", "1")
+    it, dt = ctx.knn2_l2f(fp["d1"], fp["d2"])
+    monkeypatch.setenv("VB_L2_TC", "0")
+    ie, de = ctx.knn2_l2f(fp["d1"], fp["d2"])
+    monkeypatch.delenv("VB_L2_TC")
+    assert np.array_equal(it, ie) and np.array_equal(bits(dt), bits(de))
+    qs = np.arange(0, n, 50)
+    oi, od = oracle.knn2_l2f(np.ascontiguousarray(fp["d1"][qs]), fp["d2"])
+    assert np.array_equal(it[qs], oi) and np.array_equal(bits(dt[qs]), bits(od))
+    prm = ctx.params(0.7, 8, H, 10.0, 77)
+    g = ctx.match_features_l2f(fp["p1"], fp["d1"], fp["p2"], fp["d2"], prm)
+    tent = ctx.match_l2f(fp["d1"], fp["d2"], 0.7)
+    keep = (dt[:, 0].astype(np.float64) < dt[:, 1].astype(np.float64) * 0.7)          # the ratio test restated on the verified kNN
+    assert np.array_equal(tent[:, 0], np.nonzero(keep)[0]) and np.array_equal(tent[:, 1], it[keep, 0])
+    o = oracle.find_fundamental(fp["p1"], fp["p2"], tent, 8, H, 10.0, 77)
+    assert g["status"] == 0 and g["n_tentative"] == len(tent) and g["best"] == o["best"] and g["n_inliers"] == o["n_inliers"]
+    assert np.array_equal(bits(g["F"]), bits(o["F"])) and np.array_equal(g["matches"], tent[o["mask"].astype(bool)])
+    assert g["n"] > 8000
+
+
+@pytest.mark.parametrize("m,H", [(1000, 256), (1000000, 256), (1000, 16384), (1000000, 16384)])
+def test_config5_corners(ctx, oracle, m, H):
+    """BASELINE configs[4] corners through vb_ransac_score (count + residual sum of every hypothesis,
+    src/RansacFilter.cpp:105-140): the oracle on a sample of hypotheses (bit-exact count and score), duplicates of a
+    hypothesis give identical outputs, counts are additive over a split of the matches."""
+    corr = synth.correspondences(m, 5)
+    bank = _hyp_bank(oracle, synth.correspondences(4000, 3), 256, 9)
+    rng = np.random.default_rng(H)
+    pick = rng.integers(0, 256, H)
+    Fs = np.ascontiguousarray(bank[pick])
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    sample = sorted(set([0, 1, H // 2, H - 1] + rng.integers(0, H, 4 if m > 100000 else 40).tolist()))
+    ocnt, osc = _oracle_scores(oracle, corr, Fs[sample], 10.0)
+    assert np.array_equal(cnt[sample], ocnt) and np.array_equal(bits(sc[sample]), bits(osc))
+    first = {}
+    for h, b in enumerate(pick):                 # every copy of a bank entry must report the same pair
+        if b in first:
+            assert cnt[h] == cnt[first[b]] and bits(sc[h:h + 1])[0] == bits(sc[first[b]:first[b] + 1])[0]
+        else:
+            first[b] = h
+    cut = m // 3
+    c1 = ctx.ransac_counts(np.ascontiguousarray(corr[:cut]), Fs, 10.0)
+    c2 = ctx.ransac_counts(np.ascontiguousarray(corr[cut:]), Fs, 10.0)
+    assert np.array_equal(cnt, c1 + c2)

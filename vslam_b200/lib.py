@@ -43,9 +43,9 @@ EXPORTS = [
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
-    "vb_match_features", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
+    "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
     "vb_host_alloc", "vb_host_free", "vb_host_register", "vb_host_unregister",
-    "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms",
+    "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms", "vb_probe_tensor_peak",
 ]
 
 
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     L.vb_ransac_sample_sets.argtypes = [vp, u32, C.c_int, u32, u32, vp]
     L.vb_ransac_residual.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp, f32, vp, C.POINTER(i32), C.POINTER(f32)]
     L.vb_match_features.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, C.POINTER(PairResult)]
+    L.vb_match_features_l2f.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, C.POINTER(PairResult)]
+    L.vb_match_features_l2f_d.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_submit.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(C.c_int)]
@@ -124,6 +126,7 @@ def load_library() -> C.CDLL:
                                           C.POINTER(u32)]
     L.vb_extract_rt.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     L.vb_triangulate.argtypes = [vp, vp, vp, u32, vp, vp, vp]
+    L.vb_probe_tensor_peak.argtypes = [vp, C.c_int, u32, u32, u32, C.POINTER(f32), C.POINTER(f64)]
     L.vb_profile_enable.argtypes = [vp, C.c_int]
     L.vb_profile_last_ms.restype = f32
     L.vb_profile_last_ms.argtypes = [vp, C.c_char_p]
@@ -174,6 +177,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.vb_launch_count(self.h))
+
+    def probe_tensor_peak(self, kind: int, n_cols: int = 256, iters: int = 4096, reps: int = 5) -> float:
+        """TFLOP/s of back-to-back tcgen05.mma of one kind (0 mxf4, 1 f8f6f4, 2 f16/bf16), nothing else running."""
+        ms, fl = C.c_float(), C.c_double()
+        self._chk(self.L.vb_probe_tensor_peak(self.h, kind, n_cols, iters, reps, C.byref(ms), C.byref(fl)))
+        return fl.value / (ms.value * 1e-3) / 1e12
 
     def profile(self, on: bool):
         self._chk(self.L.vb_profile_enable(self.h, int(on)))
@@ -299,6 +308,15 @@ class Context:
         out, res = np.zeros((max(len(d1), 1), 2), np.int32), PairResult()
         self._chk(self.L.vb_match_features(self.h, _ptr(p1), _ptr(d1), len(d1), _ptr(p2), _ptr(d2), len(d2), d1.shape[1],
                                            C.byref(prm), _ptr(out), C.byref(res)))
+        return dict(status=res.status, n=res.n_matches, matches=out[:max(res.n_matches, 0)].copy(),
+                    F=np.array(res.F, np.float32).reshape(3, 3), n_tentative=res.n_tentative, best=res.best_hyp,
+                    n_inliers=res.n_inliers, score=np.float32(res.score))
+
+    def match_features_l2f(self, p1, d1, p2, d2, prm: PairParams):
+        p1, p2, d1, d2 = _f32(p1), _f32(p2), _f32(d1), _f32(d2)
+        out, res = np.zeros((max(len(d1), 1), 2), np.int32), PairResult()
+        self._chk(self.L.vb_match_features_l2f(self.h, _ptr(p1), _ptr(d1), len(d1), _ptr(p2), _ptr(d2), len(d2), d1.shape[1],
+                                               C.byref(prm), _ptr(out), C.byref(res)))
         return dict(status=res.status, n=res.n_matches, matches=out[:max(res.n_matches, 0)].copy(),
                     F=np.array(res.F, np.float32).reshape(3, 3), n_tentative=res.n_tentative, best=res.best_hyp,
                     n_inliers=res.n_inliers, score=np.float32(res.score))
