@@ -285,6 +285,15 @@ int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points,
 int vb_extract_rt(vb_ctx *ctx, const float *F, uint32_t P, const float *K, float *R, float *t, float *E_out);
 int vb_triangulate(vb_ctx *ctx, const float *p1, const float *p2, uint32_t n, const float *c1, const float *c2,
                    float *points4);
+/* triangulate + the reprojection gate that consumes it (reference src/vslam.cpp:186-251), fused: points4 [n][4] as above;
+ * re1 / re2 [n] = squared reprojection error in camera 1 / 2 (`d.row(i).dot(d.row(i))`, :240, :242) of every row; inlier_idx
+ * = the rows pushed to reprojection_inliers, in order: map_point_ids[i] <= 0 (or map_point_ids == NULL), re1 <= threshold_sq
+ * and re2 <= threshold_sq (thresholdSq = 4, :53); *reproj_error = the f64 running sum of (re1 + re2) over them (:249).
+ * Kept as written: the loop that makes the reprojections non-homogeneous (:201-211) only reaches the first ceil(n/3) rows,
+ * and a NaN error passes the gate. Any output except n_inliers may be NULL. */
+int vb_triangulate_gated(vb_ctx *ctx, const float *p1, const float *p2, uint32_t n, const float *c1, const float *c2,
+                         const int32_t *map_point_ids, float threshold_sq, float *points4, float *re1, float *re2,
+                         uint32_t *inlier_idx, uint32_t *n_inliers, double *reproj_error);
 
 /* ------------------------------------------------------------------------------------------------
  * Timing hook for bench.py: CUDA-event time (ms) of the kernels of one class recorded on the context's

@@ -746,6 +746,55 @@ void vbo_triangulate(const float *p1, const float *p2, int n, const float *c1, c
     }
 }
 
+/* Reprojection gate after triangulation, src/vslam.cpp:186-251 as written:
+ *   reproj_k = points_4d * c_k.t()            :192-193  (cv::gemm GEMM_2_T on an n x 4 by 3 x 4: vbo_project_points' rule)
+ *   for (i = 0; i < reproj.rows; i += 3)      :201-211  the loop counts ROWS but indexes the FLAT data, so it divides
+ *       data[i] /= h, data[i+1] /= h, h = 1             x, y by h only for the first ceil(n / 3) points; the rest keep
+ *                                                       their raw homogeneous x, y. Reproduced, not repaired.
+ *   d_k = reproj_k.colRange(0, 2) - initial_points_k    :231-232  fp32 subtraction
+ *   per row i:                                          :237-251
+ *       if (map_point_ids[i] > 0) continue              (strictly positive: id 0 is NOT skipped; indexed by ROW)
+ *       re1 = d1.row(i).dot(d1.row(i))                  cv::Mat::dot on two floats: products and the sum in double
+ *       if (re1 > thresholdSq) continue                 (dotProd_32f's scalar tail), result narrowed to f32;
+ *       re2 likewise; if (re2 > thresholdSq) continue   NaN compares false, so a NaN error PASSES the gate
+ *       reprojection_inliers.push_back(i); reproj_error += re1 + re2   (f32 add, accumulated in f64, row order)
+ * The Mat::dot rule is restated from OpenCV's source (there is no Python binding to pin it with); everything else is
+ * pinned by cv2 goldens (tests/golden/gen_golden_gate.py). re1 / re2 are reported for every row. Returns the inlier count. */
+int vbo_reprojection_gate(const float *points4, int n, const float *c1, const float *c2, const float *ip1, const float *ip2,
+                          const int32_t *map_point_ids, float threshold_sq, float *re1_out, float *re2_out,
+                          int32_t *inlier_idx, double *reproj_error) {
+    float *r1 = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
+    float *r2 = (float *)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
+    vbo_project_points(points4, n, c1, r1);
+    vbo_project_points(points4, n, c2, r2);
+    for (size_t i = 0; i < (size_t)n; i += 3) {
+        const float h1 = r1[i + 2];
+        r1[i] = r1[i] / h1; r1[i + 1] = r1[i + 1] / h1; r1[i + 2] = 1.0f;
+        const float h2 = r2[i + 2];
+        r2[i] = r2[i] / h2; r2[i + 1] = r2[i + 1] / h2; r2[i + 2] = 1.0f;
+    }
+    int cnt = 0;
+    double err = 0.0;
+    for (int i = 0; i < n; i++) {
+        const float d1x = r1[3 * i] - ip1[2 * i], d1y = r1[3 * i + 1] - ip1[2 * i + 1];
+        const float d2x = r2[3 * i] - ip2[2 * i], d2y = r2[3 * i + 1] - ip2[2 * i + 1];
+        const float re1 = (float)((double)d1x * (double)d1x + (double)d1y * (double)d1y);
+        const float re2 = (float)((double)d2x * (double)d2x + (double)d2y * (double)d2y);
+        if (re1_out) re1_out[i] = re1;
+        if (re2_out) re2_out[i] = re2;
+        if (map_point_ids && map_point_ids[i] > 0) continue;
+        if (re1 > threshold_sq) continue;
+        if (re2 > threshold_sq) continue;
+        if (inlier_idx) inlier_idx[cnt] = i;
+        cnt++;
+        err += (double)(re1 + re2);
+    }
+    if (reproj_error) *reproj_error = err;
+    free(r1);
+    free(r2);
+    return cnt;
+}
+
 /* ============================ seed hook ======================================================= */
 
 static unsigned g_ref_seed = 0;

@@ -143,6 +143,10 @@ void vbo_essential(const float *F, const float *K, float *E);
 void vbo_extract_rt(const float *F, const float *K, float *R, float *t);
 void vbo_null_vector_4x4(const float *A, float *v4);
 void vbo_triangulate(const float *p1, const float *p2, int n, const float *c1, const float *c2, float *out);
+/* src/vslam.cpp:186-251: reprojection into both cameras, the (partial, as written) dehomogenisation, squared errors, gate. */
+int vbo_reprojection_gate(const float *points4, int n, const float *c1, const float *c2, const float *ip1, const float *ip2,
+                          const int32_t *map_point_ids, float threshold_sq, float *re1_out, float *re2_out,
+                          int32_t *inlier_idx, double *reproj_error);
 
 /* ---- seed hook consumed by the cvlite random_device stand-in (oracle/_ref builds only) -------- */
 void vbo_ref_seed_set(unsigned seed);

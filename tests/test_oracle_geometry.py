@@ -101,3 +101,23 @@ def test_extract_rt_exactly_singular_essential(oracle):
         assert abs(float(np.linalg.norm(to.astype(np.float64))) - 1.0) < 1e-6
         assert min(np.abs(to - t).max(), np.abs(to + t).max()) < 2e-6
         assert np.abs(np.abs(Ro) - np.abs(R)).max() < 2e-6 and np.linalg.det(Ro.astype(np.float64)) > 0.999
+
+
+GATE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gate_cv2_4_13.npz"))
+GATE_TAGS = ("n1", "n3", "n4", "n98", "n99", "n100", "n101", "n1500")
+
+
+def test_reprojection_gate_bit_exact_vs_cv2(oracle):
+    """src/vslam.cpp:186-251 replayed with cv2 (tests/golden/gen_golden_gate.py): squared reprojection errors bit for bit on
+    both sides of cv::gemm's 100-row switch, the inlier list and the f64 error sum exactly — including the reference's
+    partial dehomogenisation (only the first ceil(n/3) rows) and its `map_point_ids[i] > 0` test."""
+    for tag in GATE_TAGS:
+        g = {k: GATE[f"{tag}_{k}"] for k in ("P4", "c1", "c2", "p1", "p2", "ids", "re1", "re2", "inl", "err")}
+        idx, re1, re2, err = oracle.reprojection_gate(g["P4"], g["c1"], g["c2"], g["p1"], g["p2"], g["ids"], 4.0)
+        assert np.array_equal(_bits(re1), _bits(g["re1"])) and np.array_equal(_bits(re2), _bits(g["re2"])), tag
+        assert np.array_equal(idx, g["inl"]) and err == float(g["err"]), tag
+    # id 0 is not "claimed" (:239 tests > 0), a missing id array gates on the errors alone
+    g = {k: GATE[f"n1500_{k}"] for k in ("P4", "c1", "c2", "p1", "p2", "ids", "inl")}
+    assert (g["ids"][g["inl"]] <= 0).all() and (g["ids"][g["inl"]] == 0).any()
+    idx_all, _, _, _ = oracle.reprojection_gate(g["P4"], g["c1"], g["c2"], g["p1"], g["p2"], None, 4.0)
+    assert set(g["inl"]).issubset(set(idx_all)) and len(idx_all) > len(g["inl"])

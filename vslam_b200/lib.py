@@ -45,7 +45,7 @@ EXPORTS = [
     "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
     "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
     "vb_host_alloc", "vb_host_free", "vb_host_register", "vb_host_unregister",
-    "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_profile_enable", "vb_profile_last_ms", "vb_probe_tensor_peak",
+    "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_triangulate_gated", "vb_profile_enable", "vb_profile_last_ms", "vb_probe_tensor_peak",
 ]
 
 
@@ -127,6 +127,7 @@ def load_library() -> C.CDLL:
     L.vb_extract_rt.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     L.vb_triangulate.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.vb_probe_tensor_peak.argtypes = [vp, C.c_int, u32, u32, u32, C.POINTER(f32), C.POINTER(f64)]
+    L.vb_triangulate_gated.argtypes = [vp, vp, vp, u32, vp, vp, vp, f32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(f64)]
     L.vb_profile_enable.argtypes = [vp, C.c_int]
     L.vb_profile_last_ms.restype = f32
     L.vb_profile_last_ms.argtypes = [vp, C.c_char_p]
@@ -253,6 +254,18 @@ class Context:
         out = np.zeros((max(len(p1), 1), 4), np.float32)
         self._chk(self.L.vb_triangulate(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(c1), _ptr(c2), _ptr(out)))
         return out[:len(p1)]
+
+    def triangulate_gated(self, p1, p2, c1, c2, ids, thr_sq=4.0):
+        """-> (points4 [n][4], inlier indices, re1 [n], re2 [n], reproj_error)."""
+        p1, p2, c1, c2 = _f32(p1), _f32(p2), _f32(c1).reshape(12), _f32(c2).reshape(12)
+        n = len(p1)
+        ids = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        re1, re2, idx = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.uint32)
+        cnt, err = C.c_uint32(), C.c_double()
+        self._chk(self.L.vb_triangulate_gated(self.h, _ptr(p1), _ptr(p2), n, _ptr(c1), _ptr(c2), _ptr(ids), thr_sq, _ptr(out),
+                                              _ptr(re1), _ptr(re2), _ptr(idx), C.byref(cnt), C.byref(err)))
+        return out[:n], idx[:cnt.value].astype(np.int32), re1[:n], re2[:n], err.value
 
     # ---- ransac ----
     def ransac_fundamental(self, p1, p2, matches, min_items=8, iters=100, thr=10.0, seed=0):
