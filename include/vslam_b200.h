@@ -125,6 +125,21 @@ int vb_ransac_fundamental(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const fl
                           const int32_t *matches, uint32_t m, int min_items, uint32_t max_iterations, float threshold,
                           uint32_t seed, float *F, uint8_t *inlier_mask, int32_t *n_inliers, float *score,
                           int32_t *best_hyp);
+/* Opt-in mode — NOT reference behaviour; flags = 0 is exactly vb_ransac_fundamental. The two defects the reference flags
+ * itself and never repaired, as explicit switches:
+ *   VB_RANSAC_HARTLEY  `//TODO: normalize` (src/RansacFilter.cpp:40): every 8-point sample is translated to its centroid and
+ *                      scaled to mean distance sqrt(2) per image before the same solve; F = T2^T F^ T1, unit Frobenius norm.
+ *   VB_RANSAC_SAMPSON  the mis-parenthesised residual (:125-126) becomes the true Sampson distance
+ *                      (x2^T F x1)^2 / (a0^2 + a1^2 + b0^2 + b1^2), a = F x1, b = F^T x2 (double, narrowed to f32 once);
+ *                      `threshold` is then in squared pixels.
+ * Sample sets, the inlier test (e <= threshold), the score and the selection rule (:59) stay the reference's. Defined
+ * operation by operation by the CPU checker's mode of the same name; bit-exact against it. */
+#define VB_RANSAC_HARTLEY 1u
+#define VB_RANSAC_SAMPSON 2u
+int vb_ransac_fundamental_ex(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,
+                             const int32_t *matches, uint32_t m, int min_items, uint32_t max_iterations, float threshold,
+                             uint32_t seed, uint32_t flags, float *F, uint8_t *inlier_mask, int32_t *n_inliers, float *score,
+                             int32_t *best_hyp);
 /* Per-hypothesis view of the same run, for parity tests: sets[iters][8], F_all[iters][9],
  * n_inliers[iters], score[iters]. Any output may be NULL. */
 int vb_ransac_hypotheses(vb_ctx *ctx, const float *p1_xy, uint32_t n1, const float *p2_xy, uint32_t n2,

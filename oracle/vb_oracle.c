@@ -311,6 +311,124 @@ int vbo_find_fundamental(const float *p1, const float *p2, const int32_t *matche
     return 0;
 }
 
+/* ============================ opt-in mode: Hartley normalisation + true Sampson distance ====== */
+/* NOT reference behaviour: the two repairs the reference itself flags and never made — `//TODO: normalize`
+ * (src/RansacFilter.cpp:40) and the mis-parenthesised residual (:125-126) — as an explicit opt-in (flags != 0). The default
+ * path above is untouched. Every operation below is one IEEE rounding in the order written; the GPU repeats it exactly.
+ *
+ * VBO_RANSAC_HARTLEY  each 8-point sample is translated to its centroid and scaled to mean distance sqrt(2) per image
+ *                     (Hartley 1997) before the same 8-point solve, and F is mapped back: F = T2^T F^ T1, unit Frobenius norm.
+ * VBO_RANSAC_SAMPSON  e = (x2^T F x1)^2 / (a0^2 + a1^2 + b0^2 + b1^2), a = F x1, b = F^T x2 — the first-order geometric
+ *                     error the reference's expression was meant to be — evaluated in double, narrowed to f32 once; the
+ *                     inlier test (e <= threshold), the score sum and the selection rule stay the reference's. */
+static void hartley_norm(const float *pts /* [8][2] */, float *out /* [8][2] */, double *s_out, double *tx, double *ty) {
+    double cx = 0.0, cy = 0.0;
+    for (int i = 0; i < 8; i++) { cx = cx + (double)pts[2 * i]; cy = cy + (double)pts[2 * i + 1]; }
+    cx = cx / 8.0; cy = cy / 8.0;
+    double md = 0.0;
+    for (int i = 0; i < 8; i++) {
+        const double dx = (double)pts[2 * i] - cx, dy = (double)pts[2 * i + 1] - cy;
+        md = md + sqrt(dx * dx + dy * dy);
+    }
+    md = md / 8.0;
+    const double s = (md > 0.0) ? 1.4142135623730951 / md : 1.0;
+    for (int i = 0; i < 8; i++) {
+        out[2 * i] = (float)(s * ((double)pts[2 * i] - cx));
+        out[2 * i + 1] = (float)(s * ((double)pts[2 * i + 1] - cy));
+    }
+    *s_out = s; *tx = s * cx; *ty = s * cy;
+}
+
+void vbo_compute_fundamental_hartley(const float *p1set, const float *p2set, float *F) {
+    float n1[16], n2[16], Fh[9];
+    double s1, tx1, ty1, s2, tx2, ty2;
+    hartley_norm(p1set, n1, &s1, &tx1, &ty1);
+    hartley_norm(p2set, n2, &s2, &tx2, &ty2);
+    vbo_compute_fundamental(n1, n2, Fh);
+    /* G = F^ T1, T = [[s, 0, -tx], [0, s, -ty], [0, 0, 1]] */
+    double G[9], R[9];
+    for (int i = 0; i < 3; i++) {
+        const double f0 = (double)Fh[3 * i], f1 = (double)Fh[3 * i + 1], f2 = (double)Fh[3 * i + 2];
+        G[3 * i] = f0 * s1;
+        G[3 * i + 1] = f1 * s1;
+        G[3 * i + 2] = (f2 - f0 * tx1) - f1 * ty1;
+    }
+    /* R = T2^T G */
+    for (int j = 0; j < 3; j++) {
+        R[j] = s2 * G[j];
+        R[3 + j] = s2 * G[3 + j];
+        R[6 + j] = (G[6 + j] - tx2 * G[j]) - ty2 * G[3 + j];
+    }
+    double nn = 0.0;
+    for (int i = 0; i < 9; i++) nn = nn + R[i] * R[i];
+    const double nrm = sqrt(nn);
+    for (int i = 0; i < 9; i++) F[i] = (float)((nrm > 0.0) ? R[i] / nrm : R[i]);
+}
+
+float vbo_sampson_one(const float *F, float x1f, float y1f, float x2f, float y2f) {
+    const double x1 = x1f, y1 = y1f, x2 = x2f, y2 = y2f;
+    double f[9];
+    for (int i = 0; i < 9; i++) f[i] = (double)F[i];
+    const double a0 = (f[0] * x1 + f[1] * y1) + f[2];
+    const double a1 = (f[3] * x1 + f[4] * y1) + f[5];
+    const double a2 = (f[6] * x1 + f[7] * y1) + f[8];
+    const double b0 = (f[0] * x2 + f[3] * y2) + f[6];
+    const double b1 = (f[1] * x2 + f[4] * y2) + f[7];
+    const double sv = (x2 * a0 + y2 * a1) + a2;
+    const double den = ((a0 * a0 + a1 * a1) + b0 * b0) + b1 * b1;
+    return (float)((sv * sv) / den);
+}
+
+int vbo_find_fundamental_ex(const float *p1, const float *p2, const int32_t *matches, int m, int min_items, int max_iterations,
+                            float threshold, uint32_t seed, unsigned flags, float *F, uint8_t *mask, int *n_inliers, float *score,
+                            int *best_hyp, float *F_all, int32_t *cnt_all, float *score_all) {
+    if (flags == 0)
+        return vbo_find_fundamental(p1, p2, matches, m, min_items, max_iterations, threshold, seed, F, mask, n_inliers, score,
+                                    best_hyp, NULL, F_all, cnt_all, score_all);
+    if (min_items < 1 || min_items > 8 || m < min_items || max_iterations < 0) return -1;
+    int32_t *sets = (int32_t *)malloc(sizeof(int32_t) * 8 * (size_t)(max_iterations > 0 ? max_iterations : 1));
+    uint8_t *cur = (uint8_t *)malloc((size_t)(m > 0 ? m : 1));
+    float *e = (float *)malloc(sizeof(float) * (size_t)(m > 0 ? m : 1));
+    vbo_initialize_sets(m, min_items, max_iterations, seed, sets);
+    float best_score = 0.0f;
+    int best_n = 0, best = -1;
+    for (int i = 0; i < max_iterations; i++) {
+        float s1[16], s2[16], Fi[9];
+        for (int j = 0; j < 8; j++) {
+            int idx = sets[i * 8 + j];
+            s1[2 * j] = p1[2 * (size_t)matches[2 * idx]];
+            s1[2 * j + 1] = p1[2 * (size_t)matches[2 * idx] + 1];
+            s2[2 * j] = p2[2 * (size_t)matches[2 * idx + 1]];
+            s2[2 * j + 1] = p2[2 * (size_t)matches[2 * idx + 1] + 1];
+        }
+        if (flags & VBO_RANSAC_HARTLEY) vbo_compute_fundamental_hartley(s1, s2, Fi);
+        else vbo_compute_fundamental(s1, s2, Fi);
+        int n = 0;
+        for (int k = 0; k < m; k++) {
+            const float *a = p1 + 2 * (size_t)matches[2 * k];
+            const float *b = p2 + 2 * (size_t)matches[2 * k + 1];
+            e[k] = (flags & VBO_RANSAC_SAMPSON) ? vbo_sampson_one(Fi, a[0], a[1], b[0], b[1])
+                                                : vbo_residual_one(Fi, a[0], a[1], b[0], b[1]);
+            cur[k] = (uint8_t)(e[k] <= threshold);
+            n += cur[k];
+        }
+        const float sc = (float)vbo_score_sum(e, m);
+        if (F_all) memcpy(F_all + 9 * (size_t)i, Fi, sizeof(Fi));
+        if (cnt_all) cnt_all[i] = n;
+        if (score_all) score_all[i] = sc;
+        if (n > best_n || (n == best_n && sc > best_score)) {
+            best_n = n; best_score = sc; best = i;
+            memcpy(F, Fi, sizeof(Fi));
+            if (mask) memcpy(mask, cur, (size_t)m);
+        }
+    }
+    if (n_inliers) *n_inliers = best_n;
+    if (score) *score = best_score;
+    if (best_hyp) *best_hyp = best;
+    free(sets); free(cur); free(e);
+    return 0;
+}
+
 /* ============================ matcher ========================================================= */
 
 static inline int hamming_bytes(const uint8_t *a, const uint8_t *b, int bytes) {

@@ -148,6 +148,16 @@ int vbo_reprojection_gate(const float *points4, int n, const float *c1, const fl
                           const int32_t *map_point_ids, float threshold_sq, float *re1_out, float *re2_out,
                           int32_t *inlier_idx, double *reproj_error);
 
+/* ---- opt-in mode (NOT reference behaviour; the default path is untouched): Hartley-normalised solve and / or the true
+ * Sampson distance, the two defects the reference flags itself (src/RansacFilter.cpp:40, :125-126). ---- */
+#define VBO_RANSAC_HARTLEY 1u
+#define VBO_RANSAC_SAMPSON 2u
+void vbo_compute_fundamental_hartley(const float *p1set, const float *p2set, float *F);
+float vbo_sampson_one(const float *F, float x1, float y1, float x2, float y2);
+int vbo_find_fundamental_ex(const float *p1, const float *p2, const int32_t *matches, int m, int min_items, int max_iterations,
+                            float threshold, uint32_t seed, unsigned flags, float *F, uint8_t *mask, int *n_inliers, float *score,
+                            int *best_hyp, float *F_all, int32_t *cnt_all, float *score_all);
+
 /* ---- seed hook consumed by the cvlite random_device stand-in (oracle/_ref builds only) -------- */
 void vbo_ref_seed_set(unsigned seed);
 unsigned vbo_ref_seed_next(void);

@@ -85,6 +85,13 @@ class Oracle:
         L.vbo_reprojection_gate.restype = C.c_int
         L.vbo_reprojection_gate.argtypes = [_f32p, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_float, _f32p, _f32p, _i32p,
                                             C.POINTER(C.c_double)]
+        L.vbo_compute_fundamental_hartley.argtypes = [_f32p, _f32p, _f32p]
+        L.vbo_sampson_one.restype = C.c_float
+        L.vbo_sampson_one.argtypes = [_f32p, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.vbo_find_fundamental_ex.restype = C.c_int
+        L.vbo_find_fundamental_ex.argtypes = [_f32p, _f32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_uint,
+                                              _f32p, _u8p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
         L.vbo_pairs_run.restype = C.c_long
         L.vbo_pairs_run.argtypes = [_f32p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float,
                                     C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -139,6 +146,25 @@ class Oracle:
         out = dict(rc=rc, F=F, mask=mask[:m], n_inliers=n.value, score=np.float32(s.value), best=b.value)
         if want_all:
             out.update(sets=sets[:iters], F_all=Fall[:iters], cnt_all=cnt[:iters], score_all=sc[:iters])
+        return out
+
+    def compute_fundamental_hartley(self, p1set, p2set):
+        F = np.zeros((3, 3), np.float32)
+        self.lib.vbo_compute_fundamental_hartley(np.ascontiguousarray(p1set, np.float32), np.ascontiguousarray(p2set, np.float32), F)
+        return F
+
+    def find_fundamental_ex(self, p1, p2, matches, min_items, iters, thr, seed, flags, want_all=False):
+        """Opt-in mode (flags: 1 = Hartley-normalised solve, 2 = true Sampson distance); flags = 0 is find_fundamental."""
+        m = len(matches)
+        matches = np.ascontiguousarray(matches, np.int32)
+        F, mask = np.zeros((3, 3), np.float32), np.zeros(max(m, 1), np.uint8)
+        n, s, b = C.c_int(), C.c_float(), C.c_int()
+        Fall, cnt, sc = np.zeros((max(iters, 1), 9), np.float32), np.zeros(max(iters, 1), np.int32), np.zeros(max(iters, 1), np.float32)
+        rc = self.lib.vbo_find_fundamental_ex(p1, p2, matches, m, min_items, iters, thr, seed, flags, F, mask, C.byref(n), C.byref(s),
+                                              C.byref(b), Fall.ctypes.data, cnt.ctypes.data, sc.ctypes.data)
+        out = dict(rc=rc, F=F, mask=mask[:m], n_inliers=n.value, score=np.float32(s.value), best=b.value)
+        if want_all:
+            out.update(F_all=Fall[:iters], cnt_all=cnt[:iters], score_all=sc[:iters])
         return out
 
     # --- matcher ---

@@ -723,3 +723,42 @@ def test_config5_corners(ctx, oracle, m, H):
     c1 = ctx.ransac_counts(np.ascontiguousarray(corr[:cut]), Fs, 10.0)
     c2 = ctx.ransac_counts(np.ascontiguousarray(corr[cut:]), Fs, 10.0)
     assert np.array_equal(cnt, c1 + c2)
+
+
+# ---------------------------------------------------------------- opt-in mode: Hartley normalisation + true Sampson distance
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("k,iters,thr", [(400, 64, 1.0), (3000, 512, 3.84), (2000, 1024, 0.5)])
+def test_optin_mode_bit_exact_vs_oracle_mode(ctx, oracle, flags, k, iters, thr):
+    """vb_ransac_fundamental_ex (NOT reference behaviour) == the oracle's mode of the same flags: winner,
+    count, score, mask and F bit for bit. flags = 0 stays the reference path (every other test in this file)."""
+    fp = synth.frame_pair(k, 31 + flags)
+    tent = oracle.match_hamming(fp["d1"], fp["d2"])
+    o = oracle.find_fundamental_ex(fp["p1"], fp["p2"], tent, 8, iters, thr, 11, flags)
+    g = ctx.ransac_fundamental(fp["p1"], fp["p2"], tent, 8, iters, thr, 11, flags=flags)
+    assert g["rc"] == 0 and g["best"] == o["best"] and g["n_inliers"] == o["n_inliers"]
+    assert np.array_equal(g["mask"], o["mask"]) and np.array_equal(bits(g["F"]), bits(o["F"]))
+    assert bits(np.array([g["score"]]))[0] == bits(np.array([o["score"]]))[0]
+    assert g["n_inliers"] > 0.5 * len(tent)
+
+
+def test_optin_mode_repairs_sideways_motion(ctx, oracle):
+    """The motion the reference's criterion is known to fail on (sideways translation): the default path finds a
+    minority of the true inliers, the opt-in mode most of them; and flags = 0 through the _ex entry IS the default path."""
+    R, t = synth._rot(0.004, -0.006, 0.003), np.array([0.35, 0.02, 0.05])
+    rng = np.random.default_rng(1)
+    k = 2000
+    p1 = np.stack([rng.uniform(0, 1280, k), rng.uniform(0, 720, k)], 1)
+    p2, _, ok = synth._advance(rng, p1, rng.uniform(4, 12, k), R, t, 0.5, 0.3)
+    p1, p2 = p1.astype(np.float32), p2.astype(np.float32)
+    mm = np.stack([np.arange(k), np.arange(k)], 1).astype(np.int32)
+    d = ctx.ransac_fundamental(p1, p2, mm, 8, 512, 10.0, 5)
+    r = ctx.ransac_fundamental(p1, p2, mm, 8, 512, 1.0, 5, flags=3)
+    assert (d["mask"].astype(bool) == ok).mean() < 0.7 < 0.85 < (r["mask"].astype(bool) == ok).mean()
+    o = oracle.find_fundamental_ex(p1, p2, mm, 8, 512, 1.0, 5, 3)
+    assert np.array_equal(r["mask"], o["mask"]) and np.array_equal(bits(r["F"]), bits(o["F"]))
+    from vslam_b200.lib import _ptr
+    F0, m0 = np.zeros((3, 3), np.float32), np.zeros(k, np.uint8)
+    n, s, b = C.c_int32(), C.c_float(), C.c_int32()
+    rc = ctx.L.vb_ransac_fundamental_ex(ctx.h, _ptr(p1), k, _ptr(p2), k, _ptr(mm), k, 8, 512, 10.0, 5, 0, _ptr(F0), _ptr(m0),
+                                        C.byref(n), C.byref(s), C.byref(b))
+    assert rc == 0 and b.value == d["best"] and np.array_equal(m0, d["mask"]) and np.array_equal(bits(F0), bits(d["F"]))

@@ -129,3 +129,32 @@ def test_projection_bit_exact_vs_cv2(oracle):
             for j in range(4):
                 r[i, j] = f(f(f(K[i, 0] * Rt[0, j]) + f(K[i, 1] * Rt[1, j])) + f(K[i, 2] * Rt[2, j]))
         assert np.array_equal(_bits(r), _bits(c2)), tag
+
+
+def test_optin_mode_is_off_by_default_and_repairs_sideways_motion(oracle):
+    """flags = 0 through vbo_find_fundamental_ex IS vbo_find_fundamental; Hartley + Sampson (flagged by the
+    reference itself at src/RansacFilter.cpp:40 and :125-126) recovers the inliers of a sideways translation, which the
+    reference's criterion cannot."""
+    from vslam_b200 import synth
+    R, t = synth._rot(0.004, -0.006, 0.003), np.array([0.35, 0.02, 0.05])
+    rng = np.random.default_rng(1)
+    k = 2000
+    p1 = np.stack([rng.uniform(0, 1280, k), rng.uniform(0, 720, k)], 1)
+    p2, _, ok = synth._advance(rng, p1, rng.uniform(4, 12, k), R, t, 0.5, 0.3)
+    p1, p2 = p1.astype(np.float32), p2.astype(np.float32)
+    mm = np.stack([np.arange(k), np.arange(k)], 1).astype(np.int32)
+    a = oracle.find_fundamental(p1, p2, mm, 8, 256, 10.0, 5)
+    b = oracle.find_fundamental_ex(p1, p2, mm, 8, 256, 10.0, 5, 0)
+    assert a["best"] == b["best"] and np.array_equal(a["mask"], b["mask"]) and np.array_equal(a["F"].view(np.uint32), b["F"].view(np.uint32))
+    r = oracle.find_fundamental_ex(p1, p2, mm, 8, 512, 1.0, 5, 3)
+    assert (a["mask"].astype(bool) == ok).mean() < 0.7 and (r["mask"].astype(bool) == ok).mean() > 0.85
+    Ft = synth.true_fundamental(R, t).reshape(-1)
+    Fr = r["F"].reshape(-1).astype(np.float64)
+    Fr /= np.linalg.norm(Fr)
+    assert min(np.linalg.norm(Fr - Ft), np.linalg.norm(Fr + Ft)) < 0.05
+    # the normalised solve of exact correspondences is the true F to fp32 accuracy where the raw-pixel solve is not
+    good = np.nonzero(ok)[0][:8]
+    X = np.stack([(p1[good, 0] - 640) / 525, (p1[good, 1] - 360) / 525, np.ones(8)], 1)
+    Fh = oracle.compute_fundamental_hartley(p1[good], p2[good])
+    assert abs(np.linalg.norm(Fh.astype(np.float64)) - 1.0) < 1e-6 and abs(np.linalg.det(Fh.astype(np.float64))) < 1e-8
+    assert X.shape == (8, 3)

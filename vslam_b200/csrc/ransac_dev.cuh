@@ -52,6 +52,7 @@ struct RansacSelectArgs {
     int2 *out_matches;      // [P][mcap] or nullptr
     int score_only;
     int prefolded;          // cnt/score already hold the folded totals (k_fold ran first)
+    int sampson;            // opt-in mode: the winner's mask uses the true Sampson distance (VB_RANSAC_SAMPSON)
     int lazy;               // counts came from k_count: no residual sums; k_select scores the tied hypotheses itself
     uint32_t *tied;         // [P][H] scratch list of tied hypotheses (lazy mode)
     const unsigned int *queue_timeouts;   // bounded counting: non-zero if a work-queue wait gave up (counts incomplete), or nullptr
@@ -63,6 +64,7 @@ int ransac_launch_score(vb_ctx *ctx, const RansacPlan &pl, const float4 *corr, P
 // lazy = true: count with k_count (approximate residual + exact fallback) and compute residual sums only for the
 // hypotheses that tie at the largest count; per-hypothesis scores of the others are then not available (0).
 int ransac_run(vb_ctx *ctx, const RansacPlan &pl, const float4 *corr, ProblemDims dims, float thr,
-               vb_pair_result *results_d, uint8_t *mask_d, const int2 *tent_d, int2 *out_matches_d, bool lazy);
+               vb_pair_result *results_d, uint8_t *mask_d, const int2 *tent_d, int2 *out_matches_d, bool lazy,
+               uint32_t flags = 0);
 
 }  // namespace vb

@@ -42,7 +42,7 @@ EXPORTS = [
     "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_build_batch_d", "vb_kdtree_free_batch", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
-    "vb_ransac_fundamental", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
+    "vb_ransac_fundamental", "vb_ransac_fundamental_ex", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
     "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
     "vb_host_alloc", "vb_host_free", "vb_host_register", "vb_host_unregister",
     "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_triangulate_gated", "vb_profile_enable", "vb_profile_last_ms", "vb_probe_tensor_peak",
@@ -94,6 +94,8 @@ def load_library() -> C.CDLL:
     L.vb_match_l2f.argtypes = [vp, vp, u32, vp, u32, u32, f64, vp, C.POINTER(u32)]
     L.vb_ransac_fundamental.argtypes = [vp, vp, u32, vp, u32, vp, u32, C.c_int, u32, f32, u32, vp, vp,
                                         C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
+    L.vb_ransac_fundamental_ex.argtypes = [vp, vp, u32, vp, u32, vp, u32, C.c_int, u32, f32, u32, u32, vp, vp,
+                                           C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
     L.vb_ransac_hypotheses.argtypes = [vp, vp, u32, vp, u32, vp, u32, C.c_int, u32, f32, u32, vp, vp, vp, vp]
     L.vb_ransac_score.argtypes = [vp, vp, u32, vp, u32, f32, vp, vp]
     L.vb_ransac_score_d.argtypes = [vp, vp, u32, vp, u32, f32, vp, vp]
@@ -268,13 +270,17 @@ class Context:
         return out[:n], idx[:cnt.value].astype(np.int32), re1[:n], re2[:n], err.value
 
     # ---- ransac ----
-    def ransac_fundamental(self, p1, p2, matches, min_items=8, iters=100, thr=10.0, seed=0):
+    def ransac_fundamental(self, p1, p2, matches, min_items=8, iters=100, thr=10.0, seed=0, flags=0):
         p1, p2, matches = _f32(p1), _f32(p2), np.ascontiguousarray(matches, np.int32)
         m = len(matches)
         F, mask = np.zeros((3, 3), np.float32), np.zeros(max(m, 1), np.uint8)
         n, s, b = C.c_int32(), C.c_float(), C.c_int32()
-        rc = self.L.vb_ransac_fundamental(self.h, _ptr(p1), len(p1), _ptr(p2), len(p2), _ptr(matches), m, min_items, iters,
-                                          thr, seed, _ptr(F), _ptr(mask), C.byref(n), C.byref(s), C.byref(b))
+        if flags:
+            rc = self.L.vb_ransac_fundamental_ex(self.h, _ptr(p1), len(p1), _ptr(p2), len(p2), _ptr(matches), m, min_items, iters,
+                                                 thr, seed, flags, _ptr(F), _ptr(mask), C.byref(n), C.byref(s), C.byref(b))
+        else:
+            rc = self.L.vb_ransac_fundamental(self.h, _ptr(p1), len(p1), _ptr(p2), len(p2), _ptr(matches), m, min_items, iters,
+                                              thr, seed, _ptr(F), _ptr(mask), C.byref(n), C.byref(s), C.byref(b))
         self._chk(rc, ok=(VB_OK, VB_ERR_TOO_FEW, VB_ERR_NO_MODEL))
         return dict(rc=rc, F=F, mask=mask[:m], n_inliers=n.value, score=np.float32(s.value), best=b.value)
 
