@@ -356,7 +356,7 @@ def main():
                 "dram_traffic_full_count_kernel": ncu_traffic("k_count", P_prof, k, args.hyps),
                 "note": "a hypothesis is abandoned only when its count so far plus every match it has not seen is below a "
                         "count another hypothesis is known to reach: winner, count, score and mask are bit-identical to "
-                        "counting everything (tests/test_gpu_bounded_count.py); VB_RANSAC_PRUNE=0 runs the full count "
+                        "counting everything (tests/test_gpu_bounded_count.py); option ransac_prune = 0 runs the full count "
                         "(k_count2, 4.05 ms on this workload)"}
     step_ms = ms_total / args.steps
     # kernel_ms covers the last batch of P_prof pairs; its share of the step is scaled to the step's P pairs
@@ -533,7 +533,7 @@ def hamming_roofline(P, k, ms, bf16_peak, peak_src, probe):
     probe's own bf16 reading are printed next to it so the method can be judged."""
     if not ms or ms <= 0:
         return None
-    fp4 = os.environ.get("VB_HAMMING_FP4", "1") != "0"
+    fp4 = "hamming_fp4=0" not in os.environ.get("VB_OPTIONS", "")
     tf = 2.0 * 256.0 * float(P) * k * k / (ms * 1e-3) / 1e12
     peak = probe["mxf4_n240"] if fp4 else probe["f8f6f4_n256"]
     return {"kernel": "k_knn2_tc4 (tcgen05 kind::mxf4, e2m1 +-1, ue8m0 2^7 scales)" if fp4 else
@@ -741,10 +741,15 @@ def config3_stage(ctx, torch, dev, orc):
     return out
 
 
-def kdtree_stage(ctx, torch, dev, pts, k):
-    """KD-tree rows of the path (not part of the pairs/s metric): one frame's tree build, k nearest queries and
-    k radius-2 queries (the search-by-projection radius, src/vslam.cpp:149) on the GPU, next to the reference's
-    own src/KDTree.cpp timed on one host core (oracle/_ref, when it travelled with the repo)."""
+def kdtree_stage(ctx, torch, dev, pts, k, nq_big=1 << 20):
+    """KD-tree rows of the path (not part of the pairs/s metric).
+    (1) One frame: tree build, k nearest queries and k radius-2 queries (the search-by-projection radius, src/vslam.cpp:149)
+        on the GPU next to the reference's own src/KDTree.cpp on one host core (oracle/_ref, when it travelled with the repo);
+        at k queries the kernels are less than one wave — these are latency figures.
+    (2) Throughput: 2^20-query batches of nearest / radius-2 against trees of k and 20 000 points, with SURVEY 8d's
+        algorithmic unit (24 * ceil(log2 N) bytes per query) against the measured HBM figure — the tree itself (12 B per
+        node) lives in L1/L2, so this is a statement of how far an irregular gather is from a streaming roofline.
+    (3) A/B of the lane mapping the north star asked about: lanes per query 1 (product), 8, 32 (option kd_lanes_per_query)."""
     p = np.ascontiguousarray(pts[1])
     rng = np.random.default_rng(0)
     q = np.ascontiguousarray(p + rng.uniform(-2, 2, p.shape), np.float32)
@@ -785,11 +790,65 @@ def kdtree_stage(ctx, torch, dev, pts, k):
             bms.append(ctx.profile_ms("kd_build"))
         L.vb_kdtree_free_batch(handles, nb)
     ctx.profile(False)
+    hbm = measured_peaks()[0]
     res["gpu_batched_build"] = {"trees": nb, "ms": float(np.mean(bms)), "trees_per_s": nb / (float(np.mean(bms)) * 1e-3),
-                                "us_per_tree": float(np.mean(bms)) * 1e3 / nb}
+                                "us_per_tree": float(np.mean(bms)) * 1e3 / nb,
+                                "algorithmic_GBps": nb * 8.0 * k * np.ceil(np.log2(k)) / (float(np.mean(bms)) * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": nb * 8.0 * k * np.ceil(np.log2(k)) / (float(np.mean(bms)) * 1e-3) / 1e9 / hbm}
     res["gpu_ms"] = {n: float(np.mean(v)) for n, v in ms.items()}
     res["gpu_queries_per_s"] = {"nearest": k / (res["gpu_ms"]["kd_nearest"] * 1e-3), "radius2": k / (res["gpu_ms"]["kd_radius"] * 1e-3)}
     res["radius2_hits"] = int(tot.value)
+
+    # ---- throughput batches and the lane-mapping A/B ------------------------------------------------------------------
+    def timed(name, call, reps=5):
+        call(); call()
+        torch.cuda.synchronize(dev)
+        v = []
+        for _ in range(reps):
+            ctx.profile(True)
+            call()
+            torch.cuda.synchronize(dev)
+            v.append(ctx.profile_ms(name))
+            ctx.profile(False)
+        return float(np.mean(v))
+
+    big = []
+    for n_tree in sorted({k, 20000}):
+        tp = np.stack([rng.uniform(0, 1280, n_tree), rng.uniform(0, 720, n_tree)], 1).astype(np.float32)
+        qq = np.ascontiguousarray(tp[rng.integers(0, n_tree, nq_big)] + rng.uniform(-3, 3, (nq_big, 2)), np.float32)
+        tp_d, qq_d = torch.from_numpy(tp).to(dev), torch.from_numpy(qq).to(dev)
+        o_pt = torch.zeros((nq_big, 2), dtype=torch.float32, device=dev)
+        o_idx = torch.zeros(nq_big, dtype=torch.int32, device=dev)
+        o_d2 = torch.zeros(nq_big, dtype=torch.float32, device=dev)
+        o_off = torch.zeros(nq_big + 1, dtype=torch.int32, device=dev)
+        o_hit = torch.zeros(8 * nq_big, dtype=torch.int32, device=dev)
+        tr = C.c_void_p()
+        build_ms = timed("kd_build", lambda: (L.vb_kdtree_free(tr) if tr else None,
+                                              ctx._chk(L.vb_kdtree_build_d(ctx.h, tp_d.data_ptr(), n_tree, C.byref(tr)))), reps=3)
+        near = lambda: ctx._chk(L.vb_kdtree_nearest_d(tr, qq_d.data_ptr(), nq_big, float("inf"), o_pt.data_ptr(), o_idx.data_ptr(), o_d2.data_ptr()))
+        rad = lambda: ctx._chk(L.vb_kdtree_radius_d(tr, qq_d.data_ptr(), nq_big, 2.0, o_off.data_ptr(), o_hit.data_ptr(), 8 * nq_big, C.byref(tot)))
+        unit = 24.0 * np.ceil(np.log2(n_tree))
+        row = {"tree_points": n_tree, "queries": nq_big, "build_ms_single_tree": build_ms,
+               "build_algorithmic_GBps": 8.0 * n_tree * np.ceil(np.log2(n_tree)) / (build_ms * 1e-3) / 1e9,
+               "algorithmic_bytes_per_query": unit}
+        ab = {}
+        for lpq in (1, 8, 32):
+            ctx.set_option("kd_lanes_per_query", lpq)
+            t_ms = timed("kd_nearest", near, reps=3 if lpq > 1 else 5)
+            ab[str(lpq)] = {"ms": t_ms, "queries_per_s": nq_big / (t_ms * 1e-3)}
+        ctx.reset_options()
+        t_near, t_rad = ab["1"]["ms"], timed("kd_radius", rad)
+        row["nearest"] = {"ms": t_near, "queries_per_s": nq_big / (t_near * 1e-3), "algorithmic_GBps": unit * nq_big / (t_near * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": unit * nq_big / (t_near * 1e-3) / 1e9 / hbm}
+        row["radius2"] = {"ms": t_rad, "queries_per_s": nq_big / (t_rad * 1e-3), "hits": int(tot.value),
+                          "algorithmic_GBps": unit * nq_big / (t_rad * 1e-3) / 1e9, "frac_of_hbm_peak": unit * nq_big / (t_rad * 1e-3) / 1e9 / hbm,
+                          "note": "count pass + scan + fill pass (CSR output)"}
+        row["lanes_per_query_ab"] = ab
+        big.append(row)
+        L.vb_kdtree_free(tr)
+    res["throughput"] = big
+    res["roofline_note"] = ("bound = latency / L1-L2 gather of a dependent chain (one node per step), not HBM: the tree (12 B per node) "
+                            "stays on chip; algorithmic_GBps uses SURVEY 8d's 24 * ceil(log2 N) B per query against hbm_peak %.0f GB/s" % hbm)
     try:
         from oracle_lib import Ref
         if Ref.available():

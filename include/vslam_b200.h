@@ -51,6 +51,22 @@ int vb_destroy(vb_ctx *ctx);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
 int vb_set_stream(vb_ctx *ctx, void *cuda_stream);
 int vb_synchronize(vb_ctx *ctx);
+/* Path selectors for tests and measurements — the library never reads the environment. Every option chooses between code
+ * paths that return the same bits (the GPU tests force each of them against the oracle); unset = the built-in rule.
+ *   hamming_tc 0/1        popcount matcher / tcgen05 matcher regardless of problem size
+ *   hamming_fp4 0         tcgen05 matcher on kind::f8f6f4 (e4m3) instead of kind::mxf4
+ *   tc_fix8 0             the matcher's fix pass always reads both candidate groups
+ *   hamming_qpt 1/2/4     queries per thread of the popcount matcher
+ *   l2_tc 0/1             float descriptors: exact SIMT kernel / bf16 tcgen05 prefilter + exact re-evaluation
+ *   ransac_lazy 0         the pair pipeline scores every hypothesis in full instead of counting
+ *   ransac_prune 0/1/2    bounded counting never / for batches that fill the machine (default) / always
+ *   prune_first_chunks, prune_first16, prune_growth16, prune_rounds, prune_item_chunks   its checkpoint schedule
+ *   count_packed 0, score_packed 0   scalar-instruction versions of the counting / scoring kernels
+ *   kd_lanes_per_query 1/8/32        k-d tree 1-NN: lanes that share one query (A/B of the thread-per-query mapping)
+ * A build with -DVB_TUNING adds timing-only options (tc_dbg, prune_ctas_per_sm, pairs_twin, pairs_split). Unknown names
+ * return VB_ERR_INVALID. vb_reset_options restores every built-in rule. */
+int vb_set_option(vb_ctx *ctx, const char *name, long long value);
+int vb_reset_options(vb_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t vb_launch_count(const vb_ctx *ctx);
 

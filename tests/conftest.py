@@ -33,3 +33,14 @@ def ref():
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "correspondence_cv2_4_13.npz"))
+
+
+@pytest.fixture(autouse=True)
+def _reset_vb_options(request):
+    """Options set with ctx.set_option (forced code paths) never leak from one test into the next."""
+    yield
+    if "ctx" in request.fixturenames:
+        try:
+            request.getfixturevalue("ctx").reset_options()
+        except Exception:
+            pass

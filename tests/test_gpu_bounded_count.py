@@ -1,8 +1,8 @@
 """Bounded counting in the pair pipeline (k_bq_init / k_count_queue): hypotheses that provably cannot reach the largest
 inlier count are abandoned early. The result of find_fundamental (src/ransac.cpp:36-66: winner, inlier count, score, F, mask
 and the compacted matches) must not change by one bit — against the same call with the bound switched off, and against the
-CPU oracle. VB_RANSAC_PRUNE=2 forces the bounded path for every batch size (by default it runs for batches that fill the
-machine), VB_PRUNE_ROUNDS / VB_PRUNE_GROWTH16 move the checkpoints, VB_PRUNE_ITEM_CHUNKS sizes the queue's work items."""
+CPU oracle. Option ransac_prune = 2 forces the bounded path for every batch size (by default it runs for batches that fill the
+machine), prune_rounds / prune_growth16 move the checkpoints, prune_item_chunks sizes the queue's work items (vb_set_option)."""
 import numpy as np
 import pytest
 
@@ -45,12 +45,12 @@ CASES = [
 
 
 @pytest.mark.parametrize("nframes,k,seed,noise,outl,iters", CASES)
-def test_bounded_counting_equals_full_counting(ctx, monkeypatch, nframes, k, seed, noise, outl, iters):
+def test_bounded_counting_equals_full_counting(ctx, nframes, k, seed, noise, outl, iters):
     pts, desc = synth.sequence(nframes, k, seed, noise_px=noise, outlier_frac=outl)
     prm = ctx.params(0.7, 8, iters, 10.0, 11 + seed)
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "0")
+    ctx.set_option("ransac_prune", 0)
     ref, mref = ctx.pairs_run(pts, desc, prm)
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "2")
+    ctx.set_option("ransac_prune", 2)
     ctx.ransac_prune_stats(reset=True)
     got, mgot = ctx.pairs_run(pts, desc, prm)
     ev, tot = ctx.ransac_prune_stats()
@@ -59,23 +59,23 @@ def test_bounded_counting_equals_full_counting(ctx, monkeypatch, nframes, k, see
 
 
 @pytest.mark.parametrize("rounds,growth16,item_chunks", [(2, 8, 1), (3, 1, 2), (5, 64, 1), (16, 2, 3), (12, 8, 64)])
-def test_bounded_counting_checkpoint_schedules(ctx, monkeypatch, rounds, growth16, item_chunks):
+def test_bounded_counting_checkpoint_schedules(ctx, rounds, growth16, item_chunks):
     pts, desc = synth.sequence(5, 3000, 21, noise_px=0.5, outlier_frac=0.3)
     prm = ctx.params(0.7, 8, 512, 10.0, 3)
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "0")
+    ctx.set_option("ransac_prune", 0)
     ref, mref = ctx.pairs_run(pts, desc, prm)
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "2")
-    monkeypatch.setenv("VB_PRUNE_ROUNDS", str(rounds))
-    monkeypatch.setenv("VB_PRUNE_GROWTH16", str(growth16))
-    monkeypatch.setenv("VB_PRUNE_ITEM_CHUNKS", str(item_chunks))
+    ctx.set_option("ransac_prune", 2)
+    ctx.set_option("prune_rounds", rounds)
+    ctx.set_option("prune_growth16", growth16)
+    ctx.set_option("prune_item_chunks", item_chunks)
     got, mgot = ctx.pairs_run(pts, desc, prm)
     assert_same_results(got, mgot, ref, mref)
 
 
-def test_bounded_counting_saves_work_and_matches_oracle(ctx, oracle, monkeypatch):
+def test_bounded_counting_saves_work_and_matches_oracle(ctx, oracle):
     pts, desc = synth.sequence(4, 2500, 31, noise_px=0.5, outlier_frac=0.3)
     prm = ctx.params(0.7, 8, 1024, 10.0, 500)
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "2")
+    ctx.set_option("ransac_prune", 2)
     ctx.ransac_prune_stats(reset=True)
     res, mm = ctx.pairs_run(pts, desc, prm)
     ev, tot = ctx.ransac_prune_stats()
@@ -88,7 +88,7 @@ def test_bounded_counting_saves_work_and_matches_oracle(ctx, oracle, monkeypatch
         assert np.array_equal(bits(res["F"][i]).reshape(-1), bits(o["F"]).reshape(-1))
 
 
-def test_bounded_counting_single_problem_entry_point(ctx, oracle, monkeypatch):
+def test_bounded_counting_single_problem_entry_point(ctx, oracle):
     """vb_ransac_fundamental (one problem) through the bounded path, including a threshold of 0 (no inliers anywhere: nothing
     can be abandoned) and random correspondences (no model stands out)."""
     fp = synth.frame_pair(1200, 41, outlier_frac=0.4)
@@ -99,7 +99,7 @@ def test_bounded_counting_single_problem_entry_point(ctx, oracle, monkeypatch):
     jm = np.stack([np.arange(900), rng.permutation(900)], 1).astype(np.int32)
     for p1, p2, m, thr in ((fp["p1"], fp["p2"], tent, 10.0), (fp["p1"], fp["p2"], tent, 0.0), (junk1, junk2, jm, 10.0),
                            (fp["p1"], fp["p2"], tent, 1e30)):
-        monkeypatch.setenv("VB_RANSAC_PRUNE", "2")
+        ctx.set_option("ransac_prune", 2)
         g = ctx.ransac_fundamental(p1, p2, m, 8, 600, thr, 17)
         o = oracle.find_fundamental(p1, p2, m, 8, 600, thr, 17)
         assert (g["rc"] == 5) == (o["best"] < 0)
@@ -111,8 +111,8 @@ def test_bounded_counting_single_problem_entry_point(ctx, oracle, monkeypatch):
         assert np.array_equal(g["mask"], o["mask"])
 
 
-def test_bounded_counting_default_rule_device_batch(ctx, monkeypatch):
-    """vb_pairs_run_d on a device-resident batch large enough for the default rule (VB_RANSAC_PRUNE unset) and for the two
+def test_bounded_counting_default_rule_device_batch(ctx):
+    """vb_pairs_run_d on a device-resident batch large enough for the default rule (option ransac_prune unset) and for the two
     batch halves on two streams: same results as the full count; and duplicated / degenerate correspondences in the batch
     (every hypothesis ties, or no hypothesis has an inlier) do not disturb the queue."""
     import ctypes as C
@@ -135,9 +135,9 @@ def test_bounded_counting_default_rule_device_batch(ctx, monkeypatch):
         ctx.synchronize()
         return res.cpu().numpy().view(PAIR_RESULT_DTYPE), out.cpu().numpy()
 
-    monkeypatch.setenv("VB_RANSAC_PRUNE", "0")
+    ctx.set_option("ransac_prune", 0)
     ref, mref = run()
-    monkeypatch.delenv("VB_RANSAC_PRUNE")
+    ctx.reset_options()
     ctx.ransac_prune_stats(reset=True)
     got, mgot = run()
     ev, tot = ctx.ransac_prune_stats()

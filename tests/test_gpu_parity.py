@@ -265,12 +265,12 @@ TC_SHAPES = [(1, 2), (1, 7), (3, 8), (5, 9), (255, 239), (256, 240), (257, 241),
 
 
 @pytest.mark.parametrize("n1,n2", TC_SHAPES)
-def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, monkeypatch, n1, n2):
+def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, n1, n2):
     """The tcgen05 matcher (k_knn2_tc4 + k_knn2_tc_fix) forced onto shapes the size heuristic would send to the popcount
     kernel: n1 != n2, n2 around the 240-column tile and the 8-column group, n2 < one tile, n1 around the 256-query block, the
     n2 = 16 384 key limit; duplicated train rows straddling group and tile boundaries (ties to the lower index).
     BFMatcher knnMatch k = 2 order, reference src/Frame.cpp:83-85; ratio test :91."""
-    monkeypatch.setenv("VB_HAMMING_TC", "1")
+    ctx.set_option("hamming_tc", 1)
     rng = np.random.default_rng(n1 * 131 + n2)
     d2 = synth.random_descriptors(rng, n2)
     d1 = synth.random_descriptors(rng, n1)
@@ -293,10 +293,10 @@ def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, monkeypatch, n1, n2):
 
 
 @pytest.mark.parametrize("k", [241, 600, 1000])
-def test_tensor_path_whole_pair_and_sequence_edge_shapes(ctx, oracle, monkeypatch, k):
+def test_tensor_path_whole_pair_and_sequence_edge_shapes(ctx, oracle, k):
     """match_features (P = 1) and a 4-frame sequence (P = 3, shared expanded frames) through the forced tensor path at sizes
     that leave a ragged last tile / query block."""
-    monkeypatch.setenv("VB_HAMMING_TC", "1")
+    ctx.set_option("hamming_tc", 1)
     pts, desc = synth.sequence(4, k, k)
     prm = ctx.params(0.7, 8, 64, 10.0, 77)
     res, out = ctx.pairs_run(pts, desc, prm)
@@ -418,6 +418,26 @@ def test_kdtree_queries_bit_exact(ctx, oracle, n):
     t.free()
 
 
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_kdtree_nearest_lane_mappings_agree(ctx, oracle, lanes):
+    """Option kd_lanes_per_query (the warp-per-query mapping of the north star, kept as an A/B): same results as the
+    thread-per-query kernel and the oracle (src/KDTree.cpp:45-71 visiting order)."""
+    rng = np.random.default_rng(lanes)
+    n = 5000
+    pts = synth.frame_pair(n, 77)["p1"]
+    pre = oracle.kdtree_build(pts)
+    t = ctx.kdtree_build(pts)
+    q = np.ascontiguousarray(pts[rng.integers(0, n, 3000)] + rng.uniform(-3, 3, (3000, 2)), np.float32)
+    pt1, idx1, d1 = t.nearest(q)
+    ctx.set_option("kd_lanes_per_query", lanes)
+    pt2, idx2, d2 = t.nearest(q)
+    assert np.array_equal(idx1, idx2) and np.array_equal(bits(d1), bits(d2)) and np.array_equal(bits(pt1), bits(pt2))
+    for i in range(0, 3000, 60):
+        slot, od2 = oracle.kdtree_nearest(pts, pre, q[i])
+        assert idx2[i] == pre[slot] and d2[i] == od2
+    t.free()
+
+
 def test_kdtree_reference_test_protocol(ctx):
     """The reference's own acceptance test (tests/test_kdtree.cpp:47-146) replayed against the GPU tree:
     integer points in [0,100)^2, nearest accepted on equal distance, radius results compared as sets."""
@@ -488,9 +508,9 @@ def _float_descriptors(kind, n1, n2, dim, seed):
                                             ("sift", 1500, 2100, 128), ("unit", 37, 2, 128), ("equal", 500, 40, 64),
                                             ("equal", 300, 1000, 128), ("sift", 700, 300, 64), ("near", 600, 900, 128),
                                             ("near", 257, 300, 64)])
-def test_knn2_l2f_tensor_path_bit_exact(ctx, oracle, monkeypatch, kind, n1, n2, dim):
+def test_knn2_l2f_tensor_path_bit_exact(ctx, oracle, kind, n1, n2, dim):
     """The tcgen05 (bf16 GEMM + exact re-evaluation) path returns the oracle's indices and distance bits."""
-    monkeypatch.setenv("VB_L2_TC", "1")
+    ctx.set_option("l2_tc", 1)
     d1, d2 = _float_descriptors(kind, n1, n2, dim, 11)
     idx, dist = ctx.knn2_l2f(d1, d2)
     oidx, odist = oracle.knn2_l2f(d1, d2)
@@ -498,12 +518,12 @@ def test_knn2_l2f_tensor_path_bit_exact(ctx, oracle, monkeypatch, kind, n1, n2, 
     assert np.array_equal(ctx.match_l2f(d1, d2, 0.7), oracle.match_l2f(d1, d2, 0.7))
 
 
-def test_knn2_l2f_tensor_path_equals_exact_kernel_at_size(ctx, oracle, monkeypatch):
+def test_knn2_l2f_tensor_path_equals_exact_kernel_at_size(ctx, oracle):
     """6000 x 7000 x 128: tensor path == exact SIMT kernel on every query, == oracle on a slice."""
     d1, d2 = _float_descriptors("unit", 6000, 7000, 128, 3)
-    monkeypatch.setenv("VB_L2_TC", "1")
+    ctx.set_option("l2_tc", 1)
     it, dt = ctx.knn2_l2f(d1, d2)
-    monkeypatch.setenv("VB_L2_TC", "0")
+    ctx.set_option("l2_tc", 0)
     ie, de = ctx.knn2_l2f(d1, d2)
     assert np.array_equal(it, ie) and np.array_equal(bits(dt), bits(de))
     oi, od = oracle.knn2_l2f(np.ascontiguousarray(d1[:200]), d2)
@@ -589,13 +609,13 @@ def test_counts_degenerate_models_and_coordinates(ctx, oracle, golden):
     assert np.array_equal(cnt, ecnt)
 
 
-def test_pipeline_lazy_scores_equal_full_scoring(ctx, oracle, monkeypatch):
+def test_pipeline_lazy_scores_equal_full_scoring(ctx, oracle):
     """vb_pairs_run with the counting kernel + tie scoring == the same call forced through full scoring, on data with many
     ties at the largest count (noise-free correspondences)."""
     pts, desc = synth.sequence(9, 1500, 3, noise_px=0.0, outlier_frac=0.2)
     prm = ctx.params(0.7, 8, 256, 10.0, 5)
     res_lazy, m_lazy = ctx.pairs_run(pts, desc, prm)
-    monkeypatch.setenv("VB_RANSAC_LAZY", "0")
+    ctx.set_option("ransac_lazy", 0)
     res_full, m_full = ctx.pairs_run(pts, desc, prm)
     for k in ("status", "n_tentative", "n_matches", "best_hyp", "n_inliers"):
         assert np.array_equal(res_lazy[k], res_full[k]), k
@@ -633,57 +653,52 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
         ctx.L.vb_kdtree_free_batch(handles, nt)
 
 
-def test_scalar_fallback_kernels_in_subprocess():
-    """k_count<2> / k_score<2> (the scalar-instruction versions kept behind VB_COUNT_PACKED=0 / VB_SCORE_PACKED=0, read once per
-    process), the fp8 matcher (VB_HAMMING_FP4=0) and the two-group fix pass on the match path (VB_TC_FIX8=0) still agree with the
-    oracle."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = r"""
-import sys, numpy as np
-sys.path[:0] = [%r, %r]
-from oracle_lib import Oracle
-from vslam_b200 import synth
-from vslam_b200.lib import Context
-ctx, orc = Context(0), Oracle()
-corr = synth.correspondences(3000, 5)
-rng = np.random.default_rng(1)
-Fs = np.stack([orc.compute_fundamental(corr[s, :2], corr[s, 2:]).reshape(-1) for s in (rng.choice(3000, 8, replace=False) for _ in range(300))])
-cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
-cnt2 = ctx.ransac_counts(corr, Fs, 10.0)
-p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
-mm = np.stack([np.arange(3000), np.arange(3000)], 1).astype(np.int32)
-for h in range(0, 300, 37):
-    _, _, n, s = orc.residual(p1, p2, mm, Fs[h].reshape(3, 3), 10.0)
-    assert cnt[h] == n == cnt2[h] and np.float32(s).view(np.uint32) == sc[h:h + 1].view(np.uint32)[0]
-assert np.array_equal(cnt, cnt2)
-fp = synth.frame_pair(2500, 3)
-g = ctx.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], ctx.params(0.7, 8, 256, 10.0, 9))
-o = orc.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], 0.7, 8, 256, 10.0, 9)
-assert g["n"] == o["n"] and np.array_equal(g["matches"], o["matches"]) and np.array_equal(g["F"].view(np.uint32), o["F"].view(np.uint32))
-print("fallback kernels ok")
-""" % (root, os.path.join(root, "tests"))
-    # second run: default kernels, but the matcher's fix pass reading both candidate groups on the match path too
-    for extra in (dict(VB_COUNT_PACKED="0", VB_SCORE_PACKED="0", VB_HAMMING_FP4="0"), dict(VB_TC_FIX8="0")):
-        env = dict(os.environ, **extra)
-        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0 and "fallback kernels ok" in r.stdout, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("opts", [dict(count_packed=0, score_packed=0, hamming_fp4=0), dict(tc_fix8=0), dict(hamming_qpt=1, hamming_tc=0),
+                                  dict(hamming_qpt=4, hamming_tc=0)])
+def test_alternative_kernels_agree_with_oracle(ctx, oracle, opts):
+    """The code paths behind vb_set_option — k_count<2> / k_score<2> (scalar-instruction versions), the fp8 matcher, the
+    two-group fix pass on the match path, the popcount matcher's queries-per-thread variants — still agree with the oracle."""
+    for name, v in opts.items():
+        ctx.set_option(name, v)
+    corr = synth.correspondences(3000, 5)
+    rng = np.random.default_rng(1)
+    Fs = np.stack([oracle.compute_fundamental(corr[s_, :2], corr[s_, 2:]).reshape(-1)
+                   for s_ in (rng.choice(3000, 8, replace=False) for _ in range(300))])
+    cnt, sc = ctx.ransac_score(corr, Fs, 10.0)
+    cnt2 = ctx.ransac_counts(corr, Fs, 10.0)
+    p1, p2 = np.ascontiguousarray(corr[:, :2]), np.ascontiguousarray(corr[:, 2:])
+    mm = np.stack([np.arange(3000), np.arange(3000)], 1).astype(np.int32)
+    for h in range(0, 300, 37):
+        _, _, n, s = oracle.residual(p1, p2, mm, Fs[h].reshape(3, 3), 10.0)
+        assert cnt[h] == n == cnt2[h] and np.float32(s).view(np.uint32) == sc[h:h + 1].view(np.uint32)[0]
+    assert np.array_equal(cnt, cnt2)
+    fp = synth.frame_pair(2500, 3)
+    g = ctx.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], ctx.params(0.7, 8, 256, 10.0, 9))
+    o = oracle.match_features(fp["p1"], fp["d1"], fp["p2"], fp["d2"], 0.7, 8, 256, 10.0, 9)
+    assert g["n"] == o["n"] and np.array_equal(g["matches"], o["matches"]) and np.array_equal(bits(g["F"]), bits(o["F"]))
+
+
+def test_options_contract(ctx):
+    from vslam_b200.lib import VbError
+    with pytest.raises(VbError) as e:
+        ctx.set_option("no_such_option", 1)
+    assert e.value.code == 1
+    with pytest.raises(VbError):
+        ctx.set_option("tc_dbg", 2)          # timing-only options exist in a -DVB_TUNING build only
 
 
 # ---------------------------------------------------------------- BASELINE configs 3 and 5 at full size
-def test_config3_full_size(ctx, oracle, monkeypatch):
+def test_config3_full_size(ctx, oracle):
     """BASELINE configs[2] as stated: 20 000 x 20 000 x 128-d float descriptors, 4 096 hypotheses. The tensor-core matcher
     equals the exact SIMT kernel on every query (indices and distance bits) and the oracle on a 400-query sample; the
     one-call whole pair equals oracle find_fundamental on that tentative list (src/Frame.cpp:83-102, src/RansacFilter.cpp:36-67)."""
     n, H = 20000, 4096
     fp = synth.frame_pair_float(n, 5)
-    monkeypatch.setenv("VB_L2_TC", "1")
+    ctx.set_option("l2_tc", 1)
     it, dt = ctx.knn2_l2f(fp["d1"], fp["d2"])
-    monkeypatch.setenv("VB_L2_TC", "0")
+    ctx.set_option("l2_tc", 0)
     ie, de = ctx.knn2_l2f(fp["d1"], fp["d2"])
-    monkeypatch.delenv("VB_L2_TC")
+    ctx.reset_options()
     assert np.array_equal(it, ie) and np.array_equal(bits(dt), bits(de))
     qs = np.arange(0, n, 50)
     oi, od = oracle.knn2_l2f(np.ascontiguousarray(fp["d1"][qs]), fp["d2"])
@@ -738,7 +753,7 @@ def test_optin_mode_bit_exact_vs_oracle_mode(ctx, oracle, flags, k, iters, thr):
     assert g["rc"] == 0 and g["best"] == o["best"] and g["n_inliers"] == o["n_inliers"]
     assert np.array_equal(g["mask"], o["mask"]) and np.array_equal(bits(g["F"]), bits(o["F"]))
     assert bits(np.array([g["score"]]))[0] == bits(np.array([o["score"]]))[0]
-    assert g["n_inliers"] > 0.5 * len(tent)
+    assert flags == 1 or g["n_inliers"] > 0.5 * len(tent)     # (with the reference residual a threshold of 1 keeps few matches)
 
 
 def test_optin_mode_repairs_sideways_motion(ctx, oracle):

@@ -6,8 +6,8 @@ import numpy as np
 from oracle_lib import Oracle
 from vslam_b200.lib import Context
 
-os.environ["VB_L2_TC"] = "1"
 ctx, orc = Context(0), Oracle()
+ctx.set_option("l2_tc", 1)
 rng = np.random.default_rng(5)
 ok = True
 for n1, n2, dim, kind in [(256, 256, 128, "unit"), (300, 700, 64, "unit"), (1000, 513, 128, "gauss"), (2000, 3000, 128, "sift"),
@@ -39,7 +39,7 @@ n, dim = 20000, 128
 d2 = rng.standard_normal((n, dim)).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
 d1 = (d2[rng.permutation(n)] + 0.05 * rng.standard_normal((n, dim))).astype(np.float32)
 for tc in ("1", "0"):
-    os.environ["VB_L2_TC"] = tc
+    ctx.set_option("l2_tc", int(tc))
     ctx.profile(True)
     for it in range(3):
         idx, dist = ctx.knn2_l2f(d1, d2)

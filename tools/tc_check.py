@@ -6,8 +6,8 @@ import numpy as np
 from oracle_lib import Oracle
 from vslam_b200.lib import Context
 
-os.environ["VB_HAMMING_TC"] = "1"
 ctx, orc = Context(0), Oracle()
+ctx.set_option("hamming_tc", 1)
 rng = np.random.default_rng(5)
 ok = True
 for n1, n2 in [(256, 256), (300, 700), (1000, 513), (5000, 5000), (37, 2)]:

@@ -109,6 +109,15 @@ struct vb_ctx {
     vb_ctx *twin = nullptr;   // second stream + second set of workspaces: vb_pairs_run alternates sub-batches between the two
     std::vector<cudaEvent_t> events;                      // untimed events for the copy/compute pipeline
     void *pairs_stream = nullptr;                         // vb_pairs_submit / vb_pairs_wait slots (stream.cu)
+    // Path selectors for tests and measurements (vb_set_option). Nothing in the library reads the environment; a twin
+    // context looks its parent's options up.
+    std::map<std::string, long long> opts;
+    const vb_ctx *opt_parent = nullptr;
+    long long opt(const char *name, long long dflt) const {
+        const vb_ctx *c = opt_parent ? opt_parent : this;
+        auto it = c->opts.find(name);
+        return it == c->opts.end() ? dflt : it->second;
+    }
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];
     uint64_t launches = 0;

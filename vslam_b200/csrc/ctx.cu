@@ -76,6 +76,33 @@ int vb_destroy(vb_ctx *c) {
     return VB_OK;
 }
 
+// Option names. The first group selects between equivalent code paths (every one returns the same bits; the GPU tests
+// force each of them); the second group exists only in a -DVB_TUNING build (measurement aids: timing floors, schedules).
+static const char *const kOptions[] = {
+    "hamming_tc", "hamming_fp4", "tc_fix8", "hamming_qpt", "l2_tc", "ransac_lazy", "ransac_prune", "prune_first_chunks",
+    "prune_first16", "prune_growth16", "prune_rounds", "prune_item_chunks", "count_packed", "score_packed", "kd_lanes_per_query",
+#ifdef VB_TUNING
+    "tc_dbg", "prune_ctas_per_sm", "pairs_twin", "pairs_split",
+#endif
+};
+
+int vb_set_option(vb_ctx *c, const char *name, long long value) {
+    VB_REQUIRE(c && name, VB_ERR_INVALID, "NULL argument");
+    for (const char *k : kOptions)
+        if (!strcmp(k, name)) {
+            c->opts[name] = value;
+            return VB_OK;
+        }
+    vb::set_error("vb_set_option: unknown option '%s'", name);
+    return VB_ERR_INVALID;
+}
+
+int vb_reset_options(vb_ctx *c) {
+    VB_REQUIRE(c != nullptr, VB_ERR_INVALID, "ctx is NULL");
+    c->opts.clear();
+    return VB_OK;
+}
+
 int vb_set_stream(vb_ctx *c, void *s) {
     VB_REQUIRE(c != nullptr, VB_ERR_INVALID, "ctx is NULL");
     c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;

@@ -234,7 +234,7 @@ int hamming_plan(vb_ctx *ctx, uint32_t P, uint32_t n1, uint32_t n2, uint32_t byt
     const uint32_t qt1 = div_up(n1, KNN_THREADS);
     pl->qpt = ((uint64_t)P * qt1 >= 16ull * ctx->sm_count && pl->W <= 8) ? 4
               : ((uint64_t)P * qt1 >= 8ull * ctx->sm_count) ? 2 : 1;
-    if (const char *e = getenv("VB_HAMMING_QPT")) pl->qpt = atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 1;
+    if (const long long e = ctx->opt("hamming_qpt", 0)) pl->qpt = e == 4 ? 4 : e == 2 ? 2 : 1;
     pl->qtiles = div_up(n1, KNN_THREADS * pl->qpt);
     // split the train set so that a small batch still fills the machine (~4 CTAs per SM)
     uint64_t want = 4ull * ctx->sm_count;
@@ -268,7 +268,7 @@ int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const
                    KnnFinishArgs fin) {
     uint32_t nsplits = pl.nsplits;
     const uint2 *part = nullptr;
-    if (hamming_tc_eligible(pl)) {
+    if (hamming_tc_eligible(ctx, pl)) {
         int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words, &part, fin.knn_idx != nullptr);
         if (rc) return rc;
         nsplits = 1;

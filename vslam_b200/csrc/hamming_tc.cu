@@ -537,23 +537,21 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows) {
     return tc::make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, TC_KBYTES, rows, 128, TC_BOX_ROWS);
 }
 
-bool hamming_tc_eligible(const HammingPlan &pl) {
+bool hamming_tc_eligible(const vb_ctx *ctx, const HammingPlan &pl) {
     if (pl.W != 8 || pl.n2 > TC_MAX_TRAIN) return false;   // the packed float key holds 14 index bits
-    if (const char *e = getenv("VB_HAMMING_TC")) return atoi(e) != 0;
+    const long long force = ctx->opt("hamming_tc", -1);
+    if (force >= 0) return force != 0;
     // below a few thousand distance tiles the popcount kernel's finer CTA granularity wins
     return (uint64_t)pl.P * pl.n1 * pl.n2 >= (1ull << 22);
 }
 
 // WS_KNN_PART = [P][TC_COLSPLIT][n1] column-part results followed by [P][n1] final keys; *final_part points at
 // the latter, which k_knn2_finish reads as a single split.
-static bool hamming_tc_use_fp4() {
-    if (const char *e = getenv("VB_HAMMING_FP4")) return atoi(e) != 0;
-    return true;
-}
+static bool hamming_tc_use_fp4(const vb_ctx *ctx) { return ctx->opt("hamming_fp4", 1) != 0; }
 
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                       const uint2 **final_part, bool need_second_index) {
-    const bool fp4 = hamming_tc_use_fp4();
+    const bool fp4 = hamming_tc_use_fp4(ctx);
     if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
@@ -601,7 +599,11 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     const uint32_t grid = nunits < (uint32_t)ctx->sm_count ? nunits : (uint32_t)ctx->sm_count;   // one persistent CTA per SM
     uint2 *part = ctx->ws[WS_KNN_PART].as<uint2>();
     uint2 *fixed = part + (size_t)P * nparts * n1;
-    static const int dbg = getenv("VB_TC_DBG") ? atoi(getenv("VB_TC_DBG")) : 0;
+#ifdef VB_TUNING
+    const int dbg = (int)ctx->opt("tc_dbg", 0);   // timing floors (results invalid): 2 = no drain, 4 = fp8 kernel without B loads
+#else
+    const int dbg = 0;
+#endif
     ctx->prof_begin("hamming");
     if (fp4)
         k_knn2_tc4<<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
@@ -609,7 +611,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
-    static const bool fix8 = !(getenv("VB_TC_FIX8") && atoi(getenv("VB_TC_FIX8")) == 0);
+    const bool fix8 = ctx->opt("tc_fix8", 1) != 0;
     if (need_second_index || !fix8)
         k_knn2_tc_fix<16><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     else

@@ -247,14 +247,20 @@ __global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// LPQ = lanes that share one query. LPQ = 1 is the product mapping (the batch dimension on the lanes). LPQ = 8 / 32 are
+// the north star's "warp-per-query traversal with shared-memory stack staging" taken literally: the exact 1-NN descent of
+// a 2-D tree is one dependent chain (load node -> compare -> push / pop), so the group's leader lane walks it with the
+// stack in shared memory and the other lanes have nothing to do. They exist so that the choice is a measurement
+// (option kd_lanes_per_query; bench.py kdtree.lanes_per_query_ab), not an argument.
+template <int LPQ>
 __global__ void __launch_bounds__(KD_Q_THREADS) k_kd_nearest(const float *__restrict__ tx, const float *__restrict__ ty,
                                                              const uint32_t *__restrict__ tidx, uint32_t n,
                                                              const float2 *__restrict__ q, uint32_t nq, float max_d2,
                                                              float2 *__restrict__ out_pt, int32_t *__restrict__ out_idx,
                                                              float *__restrict__ out_d2) {
-    __shared__ uint2 stack[KD_MAX_DEPTH][KD_Q_THREADS];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
-    if (i >= nq) return;
+    __shared__ uint2 stack[KD_MAX_DEPTH][KD_Q_THREADS / LPQ];
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / LPQ, t = threadIdx.x / LPQ;
+    if (i >= nq || (threadIdx.x % LPQ) != 0) return;
     const float2 qp = q[i];
     float best = max_d2;
     int best_slot = -1;
@@ -595,9 +601,18 @@ int vb_kdtree_nearest_d(vb_tree *t, const float *q_d, uint32_t nq, float max_d2,
     vb_ctx *ctx = t->ctx;
     VB_CUDA(cudaSetDevice(ctx->device));
     ctx->prof_begin("kd_nearest");
-    k_kd_nearest<<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(
-        t->x, t->y, t->idx, t->n, reinterpret_cast<const float2 *>(q_d), nq, max_d2, reinterpret_cast<float2 *>(out_pt_d),
-        out_idx_d, out_d2_d);
+    const float2 *q2 = reinterpret_cast<const float2 *>(q_d);
+    float2 *op = reinterpret_cast<float2 *>(out_pt_d);
+    const long long lpq = ctx->opt("kd_lanes_per_query", 1);
+    if (lpq == 32)
+        k_kd_nearest<32><<<(unsigned)div_up64((size_t)nq * 32, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(
+            t->x, t->y, t->idx, t->n, q2, nq, max_d2, op, out_idx_d, out_d2_d);
+    else if (lpq == 8)
+        k_kd_nearest<8><<<(unsigned)div_up64((size_t)nq * 8, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(
+            t->x, t->y, t->idx, t->n, q2, nq, max_d2, op, out_idx_d, out_d2_d);
+    else
+        k_kd_nearest<1><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q2, nq, max_d2, op,
+                                                                                   out_idx_d, out_d2_d);
     ctx->prof_end("kd_nearest");
     ctx->launches++;
     VB_CUDA(cudaGetLastError());

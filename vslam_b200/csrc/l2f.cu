@@ -15,7 +15,7 @@
 namespace vb {
 
 // tensor-core path (l2f_tc.cu): same results, large problems
-bool l2_tc_eligible(uint32_t n1, uint32_t n2, uint32_t dim);
+bool l2_tc_eligible(const vb_ctx *ctx, uint32_t n1, uint32_t n2, uint32_t dim);
 int l2_tc_launch(vb_ctx *ctx, const float *d1, uint32_t n1, const float *d2, uint32_t n2, uint32_t dim, ulonglong2 *out);
 
 constexpr int L2_THREADS = 128;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_l2_finish(const ulonglong2 *__restrict_
 static int l2_device(vb_ctx *ctx, const float *d1_d, uint32_t n1, const float *d2_d, uint32_t n2, uint32_t dim, double ratio,
                      const float2 *p1_d, const float2 *p2_d) {
     int rc;
-    const bool use_tc = l2_tc_eligible(n1, n2, dim);
+    const bool use_tc = l2_tc_eligible(ctx, n1, n2, dim);
     const uint32_t qtiles = div_up(n1, L2_THREADS);
     uint32_t ns = use_tc ? 1 : div_up(4u * ctx->sm_count, qtiles);
     const uint32_t max_splits = div_up(n2, L2_TILE);

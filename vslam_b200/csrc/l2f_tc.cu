@@ -396,9 +396,10 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_l2_rerank(const float *__rest
 }
 
 // ---- host --------------------------------------------------------------------------------------------
-bool l2_tc_eligible(uint32_t n1, uint32_t n2, uint32_t dim) {
+bool l2_tc_eligible(const vb_ctx *ctx, uint32_t n1, uint32_t n2, uint32_t dim) {
     if (dim != 64 && dim != 128) return false;
-    if (const char *e = getenv("VB_L2_TC")) return atoi(e) != 0;
+    const long long force = ctx->opt("l2_tc", -1);
+    if (force >= 0) return force != 0;
     return (uint64_t)n1 * n2 >= (1ull << 22);
 }
 

@@ -74,8 +74,12 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     // the caller's stream ends by waiting for the twin.
     // Off by default since the counting stage became one persistent kernel per batch: its fixed cost (the rounds of the last
     // problems, ~0.09 ms) is paid per launch and two halves no longer overlap anything else — 5.13 ms whole against 5.20 ms
-    // split per 1 024 pairs. VB_PAIRS_SPLIT=1 restores the split.
-    static const bool use_twin = getenv("VB_PAIRS_SPLIT") && atoi(getenv("VB_PAIRS_SPLIT")) != 0;
+    // split per 1 024 pairs. The split survives as option pairs_split of a -DVB_TUNING build.
+#ifdef VB_TUNING
+    const bool use_twin = ctx->opt("pairs_split", 0) != 0;
+#else
+    const bool use_twin = false;
+#endif
     // (not while the profiling brackets are on: they time the context's own stream, one whole batch at a time)
     const bool split = use_twin && !ctx->profile && P >= 512;
     const uint32_t batch = split ? (P < 2 * PAIRS_MAX_BATCH ? (P + 1) / 2 : PAIRS_MAX_BATCH) : PAIRS_MAX_BATCH;
@@ -91,6 +95,7 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
                 return VB_ERR_CUDA;
             }
             t->stream = t->own_stream;
+            t->opt_parent = ctx;
             ctx->twin = t;
         }
         while (ctx->events.size() < 2) {
@@ -147,6 +152,7 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
         if (P - cut.back() > 256) cut.push_back(P - 192);
     }
     cut.push_back(P);
+#ifdef VB_TUNING
     if (const char *e = getenv("VB_PAIRS_SCHEDULE")) {   // measurement override: comma-separated sub-batch sizes
         cut.assign(1, 0u);
         for (const char *q = e; *q && cut.back() < P;) {
@@ -157,6 +163,7 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
         }
         if (cut.back() < P) cut.push_back(P);
     }
+#endif
     const uint32_t nb = (uint32_t)cut.size() - 1;
     if (!ctx->copy_in) {
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -164,7 +171,11 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     }
     // Odd sub-batches run on a twin context (its own stream and workspaces) so that the tail of one sub-batch's kernels
     // overlaps the head of the next one's: sub-batches are too small to fill the machine through every kernel.
-    static const bool use_twin = !(getenv("VB_PAIRS_TWIN") && atoi(getenv("VB_PAIRS_TWIN")) == 0);
+#ifdef VB_TUNING
+    const bool use_twin = ctx->opt("pairs_twin", 1) != 0;
+#else
+    const bool use_twin = true;
+#endif
     if (use_twin && nb > 1 && !ctx->twin) {
         vb_ctx *t = new vb_ctx();
         t->device = ctx->device;
@@ -175,6 +186,7 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
             return VB_ERR_CUDA;
         }
         t->stream = t->own_stream;
+        t->opt_parent = ctx;
         ctx->twin = t;
     }
     while (ctx->events.size() < 2 * (size_t)nb + 1) {

@@ -38,7 +38,7 @@ PAIR_RESULT_DTYPE = np.dtype([("status", "<i4"), ("n_tentative", "<i4"), ("n_mat
 assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 60
 
 EXPORTS = [
-    "vb_version", "vb_last_error", "vb_create", "vb_destroy", "vb_set_stream", "vb_synchronize", "vb_launch_count",
+    "vb_version", "vb_last_error", "vb_create", "vb_destroy", "vb_set_stream", "vb_set_option", "vb_reset_options", "vb_synchronize", "vb_launch_count",
     "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_build_batch_d", "vb_kdtree_free_batch", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
@@ -70,6 +70,8 @@ def load_library() -> C.CDLL:
     L.vb_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.vb_destroy.argtypes = [vp]
     L.vb_set_stream.argtypes = [vp, vp]
+    L.vb_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.vb_reset_options.argtypes = [vp]
     L.vb_synchronize.argtypes = [vp]
     L.vb_launch_count.restype = u64
     L.vb_launch_count.argtypes = [vp]
@@ -155,6 +157,11 @@ class Context:
             raise VbError(rc, self.L.vb_last_error().decode())
         self.h = h
         self.device = device
+        # tools/ convenience (Python plumbing only — the library itself never reads the environment):
+        # VB_OPTIONS="hamming_tc=1,prune_rounds=6" applies vb_set_option to every context this process creates
+        for kv in filter(None, os.environ.get("VB_OPTIONS", "").split(",")):
+            name, _, val = kv.partition("=")
+            self.set_option(name.strip(), int(val))
 
     def close(self):
         if getattr(self, "h", None):
@@ -174,6 +181,13 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._chk(self.L.vb_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_option(self, name: str, value: int):
+        """Force one of the equivalent code paths (include/vslam_b200.h, vb_set_option)."""
+        self._chk(self.L.vb_set_option(self.h, name.encode(), int(value)))
+
+    def reset_options(self):
+        self._chk(self.L.vb_reset_options(self.h))
 
     def synchronize(self):
         self._chk(self.L.vb_synchronize(self.h))
