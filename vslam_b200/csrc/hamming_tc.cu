@@ -92,9 +92,13 @@ __device__ __forceinline__ void offer2(float a, float b, float &r0, float &r1) {
     r1 = min3(r1, fmaxf(r0, lo), hi);
     r0 = fminf(r0, lo);
 }
+__device__ __forceinline__ void offer1(float a, float &r0, float &r1) {
+    r1 = fminf(r1, fmaxf(r0, a));
+    r0 = fminf(r0, a);
+}
 template <int C0, bool MASKED, int NCOLS = 32>
 __device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[NCOLS], uint32_t nvalid, float base, float &r0, float &r1) {
-    static_assert(NCOLS == 32 || NCOLS == 16, "whole pairs of 8-column groups");
+    static_assert(NCOLS == 32 || NCOLS == 16 || NCOLS == 8, "whole 8-column groups");
     float g[NCOLS / 8];
 #pragma unroll
     for (int j = 0; j < NCOLS / 8; j++) {
@@ -107,8 +111,12 @@ __device__ __forceinline__ void drain_chunk(const uint32_t (&raw)[NCOLS], uint32
         const float vmax = fmaxf(max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), v[6]), v[7]);
         g[j] = __fadd_rn(__fsub_rn((float)(C0 + 8 * j), vmax), base);   // group key: first column of the group - 2^14 * best dot
     }
+    if (NCOLS == 8) {
+        offer1(g[0], r0, r1);
+    } else {
 #pragma unroll
-    for (int j = 0; j < NCOLS / 8; j += 2) offer2(g[j], g[j + 1], r0, r1);
+        for (int j = 0; j + 1 < NCOLS / 8; j += 2) offer2(g[j], g[j + 1], r0, r1);
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -316,6 +324,12 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
     *reinterpret_cast<uint4 *>(dst + ((size_t)p * rows * 8 + t) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// DRAIN selects how a draining warp moves its 64-column part of an accumulator out of TMEM:
+//   0  the whole part in one go (two x32 loads), accumulator handed back, then the max trees — TMEM reads (480 clk per
+//      accumulator at 64 B/clk per scheduler) and ALU work (420 clk) of a step run one after the other.
+//   1  16-column slices through two rotating 16-register buffers: slice s+1 is in flight while slice s is reduced, so the
+//      TMEM port and the ALU pipe of a scheduler overlap inside a step, and half as many raw registers are live.
+template <int DRAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
            uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
@@ -340,7 +354,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4 * T4_PARTS);   // every draining warp reads a part of every accumulator
+            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : 4 * T4_PARTS);   // draining warps that read each accumulator
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
@@ -421,6 +435,148 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         const uint32_t cw = wide ? 64 : T4_NCOLS - 192;
         uint32_t raw0[32], raw1[32];
         uint32_t g = 0;
+        if (DRAIN == 3) {
+            // Dedicated warps: of the four draining warps on a scheduler (= TMEM lane quadrant) two serve accumulator 0
+            // and two accumulator 1, each taking 120 of its accumulator's 240 columns in 16-column slices (the register
+            // scoreboard lets slice s+1 load while slice s is reduced). The two accumulators fill half a step apart, so the
+            // scheduler's TMEM port and ALU pipe are reading / reducing one accumulator while the tensor pipe writes the
+            // other, instead of every warp loading both accumulators and then reducing both in lock-step.
+            const uint32_t acc = (ew >> 2) & 1u, halfc = ew >> 3;          // which accumulator, which 120-column half
+            const uint32_t hc0 = halfc * 120u;
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+            uint32_t(&rl)[8] = *reinterpret_cast<uint32_t(*)[8]>(raw1);
+            const uint32_t taddr = acc0 + ((quad * 32u) << 16) + acc * T4_NCOLS + hc0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + acc * 128 + quad * 32 + lane;
+                float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
+                float tbase = (float)hc0 + TC_KEY_BIAS;
+                for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)T4_NCOLS) {
+                    const uint32_t tile0 = j * T4_NCOLS + hc0;
+                    const bool dead = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + 120u > n2;
+                    const uint32_t nvalid = dead ? 0 : n2 - tile0;
+                    mbar_wait(bar_tfull + 8 * acc, g & 1);
+                    tc_fence_after();
+                    if (dead) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        continue;
+                    }
+#define VB_SLICE(C, BUF, NEXT_LD)                                                                   \
+                    tmem_wait_ld_regs16(BUF);                                                       \
+                    NEXT_LD;                                                                        \
+                    if (masked) drain_chunk<C, true, 16>(BUF, nvalid, tbase, r0, r1);               \
+                    else drain_chunk<C, false, 16>(BUF, nvalid, tbase, r0, r1);
+                    tmem_ld16(taddr, ra);
+                    VB_SLICE(0, ra, tmem_ld16(taddr + 16, rb))
+                    VB_SLICE(16, rb, tmem_ld16(taddr + 32, ra))
+                    VB_SLICE(32, ra, tmem_ld16(taddr + 48, rb))
+                    VB_SLICE(48, rb, tmem_ld16(taddr + 64, ra))
+                    VB_SLICE(64, ra, tmem_ld16(taddr + 80, rb))
+                    VB_SLICE(80, rb, tmem_ld16(taddr + 96, ra))
+                    // last two slices: 16 + 8 columns; the accumulator goes back once both have landed
+                    tmem_wait_ld_regs16(ra);
+                    tmem_ld8(taddr + 112, rl);
+                    if (masked) drain_chunk<96, true, 16>(ra, nvalid, tbase, r0, r1);
+                    else drain_chunk<96, false, 16>(ra, nvalid, tbase, r0, r1);
+                    tmem_wait_ld_regs8(rl);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (masked) drain_chunk<112, true, 8>(rl, nvalid, tbase, r0, r1);
+                    else drain_chunk<112, false, 8>(rl, nvalid, tbase, r0, r1);
+#undef VB_SLICE
+                }
+                if (q < n1) {
+                    uint32_t out[2];
+                    const float ks[2] = {r0, r1};
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint32_t ki = __float2uint_rz(ks[i]);
+                        out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                    : 0xffffffffu;
+                    }
+                    part[((size_t)p * 2 + halfc) * n1 + q] = make_uint2(out[0], out[1]);
+                }
+            }
+        } else if (DRAIN == 2) {
+            // Slices as in DRAIN 1, and the pipeline also runs ACROSS steps: as soon as a step's last slice has landed the
+            // accumulator goes back to the MMA warp, the first slice of the next step (the other accumulator) is requested,
+            // and only then is the last slice reduced — the TMEM port never waits for the ALU pipe inside a unit.
+            // Every part issues four slice loads per step so that the two buffers keep their roles; the fourth slice of the
+            // narrow part (columns 192..239 = three slices) re-reads its third and is not reduced.
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+            const uint32_t lane_base = acc0 + ((quad * 32u) << 16) + c0;
+            const uint32_t last_off = wide ? 48u : 32u;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
+                float r0[2] = {TC_KEY_NONE, TC_KEY_NONE}, r1[2] = {TC_KEY_NONE, TC_KEY_NONE};
+                float tbase = (float)c0 + TC_KEY_BIAS;
+                mbar_wait(bar_tfull, g & 1);   // first step of the unit: accumulator 0 of tile 0
+                tc_fence_after();
+                tmem_ld16(lane_base, ra);
+                for (uint32_t j = 0; j < ntiles; j++, tbase += (float)T4_NCOLS) {
+                    const uint32_t tile0 = j * T4_NCOLS + c0;
+                    const bool dead = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + cw > n2;
+                    const uint32_t nvalid = dead ? 0 : n2 - tile0;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t taddr = lane_base + h * T4_NCOLS;
+                        tmem_wait_ld_regs16(ra);
+                        tmem_ld16(taddr + 16, rb);
+                        if (!dead) {
+                            if (masked) drain_chunk<0, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<0, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                        }
+                        tmem_wait_ld_regs16(rb);
+                        tmem_ld16(taddr + 32, ra);
+                        if (!dead) {
+                            if (masked) drain_chunk<16, true, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<16, false, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                        }
+                        tmem_wait_ld_regs16(ra);
+                        tmem_ld16(taddr + last_off, rb);
+                        if (!dead) {
+                            if (masked) drain_chunk<32, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<32, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                        }
+                        tmem_wait_ld_regs16(rb);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                        if (h == 1) g++;
+                        if (h == 0 || j + 1 < ntiles) {   // next step: the other accumulator (this tile's, or the next tile's)
+                            mbar_wait(bar_tfull + 8 * (h ^ 1), g & 1);
+                            tc_fence_after();
+                            tmem_ld16(lane_base + (h ^ 1) * T4_NCOLS, ra);
+                        }
+                        if (wide && !dead) {
+                            if (masked) drain_chunk<48, true, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<48, false, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t q = qb + h * 128;
+                    if (q < n1) {
+                        uint32_t out[2];
+                        const float ks[2] = {r0[h], r1[h]};
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const uint32_t ki = __float2uint_rz(ks[i]);
+                            out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                        : 0xffffffffu;
+                        }
+                        part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(out[0], out[1]);
+                    }
+                }
+            }
+        } else
         for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
             const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
             float r0[2] = {TC_KEY_NONE, TC_KEY_NONE}, r1[2] = {TC_KEY_NONE, TC_KEY_NONE};   // per row half
@@ -435,6 +591,44 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                     const uint32_t taddr = acc0 + ((quad * 32u) << 16) + h * T4_NCOLS + c0;
                     mbar_wait(bar_tfull + 8 * h, g & 1);
                     tc_fence_after();
+                    if (DRAIN == 1) {
+                        if (skip) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                            continue;
+                        }
+                        uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+                        uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+                        // slices: [0,16) [16,32) [32,48) and, for the three wide parts, [48,64)
+                        tmem_ld16(taddr, ra);
+                        tmem_wait_ld_regs16(ra);
+                        tmem_ld16(taddr + 16, rb);
+                        if (masked) drain_chunk<0, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                        else drain_chunk<0, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                        tmem_wait_ld_regs16(rb);
+                        tmem_ld16(taddr + 32, ra);
+                        if (masked) drain_chunk<16, true, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                        else drain_chunk<16, false, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                        tmem_wait_ld_regs16(ra);
+                        if (wide) {
+                            tmem_ld16(taddr + 48, rb);
+                            if (masked) drain_chunk<32, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<32, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            tmem_wait_ld_regs16(rb);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                        if (wide) {
+                            if (masked) drain_chunk<48, true, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<48, false, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                        } else {
+                            if (masked) drain_chunk<32, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            else drain_chunk<32, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                        }
+                        continue;
+                    }
                     if (!skip) {
                         tmem_ld32(taddr, raw0);
                         if (wide) {
@@ -554,7 +748,10 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     const bool fp4 = hamming_tc_use_fp4(ctx);
     if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         ctx->func_attr_done |= 1u;
     }
     const uint32_t P = pl.P, n1 = pl.n1, n2 = pl.n2;
@@ -563,7 +760,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    const uint32_t nparts = fp4 ? T4_PARTS : TC_COLSPLIT;
+    const int drain = (int)ctx->opt("tc_drain", 1);
+    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
@@ -605,8 +803,14 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     const int dbg = 0;
 #endif
     ctx->prof_begin("hamming");
-    if (fp4)
-        k_knn2_tc4<<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    if (fp4 && drain == 3)
+        k_knn2_tc4<3><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 2)
+        k_knn2_tc4<2><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 1)
+        k_knn2_tc4<1><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4)
+        k_knn2_tc4<0><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else
         k_knn2_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     ctx->prof_end("hamming");

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(KD_Q_THREADS) k_kd_radius(const float *__restr
                                                             const float2 *__restrict__ q, uint32_t nq, float radius,
                                                             uint32_t *__restrict__ counts,
                                                             const uint32_t *__restrict__ offsets,
-                                                            uint32_t *__restrict__ out_idx) {
+                                                            uint32_t *__restrict__ out_idx, uint32_t out_cap = 0xffffffffu) {
     __shared__ uint2 stack[KD_MAX_DEPTH][KD_Q_THREADS];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
     if (i >= nq) return;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(KD_Q_THREADS) k_kd_radius(const float *__restr
                 const float dx = __fsub_rn(qp.x, x), dy = __fsub_rn(qp.y, y);
                 const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                 if (d2 < r2) {                                  // :91
-                    if (FILL) out_idx[off + cnt] = tidx[slot];
+                    if (FILL && off + cnt < out_cap) out_idx[off + cnt] = tidx[slot];
                     cnt++;
                 }
                 if (rlen > 0) { stack[sp][t] = make_uint2(slot + 1 + llen, rlen | ((axis ^ 1u) << 30)); sp++; }
@@ -370,6 +370,62 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *__restrict__ 
         out[n] = (uint32_t)all;
         *total = all;
     }
+}
+
+// Large query batches: the same exclusive scan in three coalesced passes (per-block scan of 4 096 counts, scan of the block
+// sums, add). The single-CTA version above walks n / 1 024 consecutive elements per thread — fine for a frame's worth of
+// queries, 1.3 ms of uncoalesced loads at 2^20.
+constexpr uint32_t SCAN_BLOCK = 4096;
+__global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out,
+                                                      uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t wt[32];
+    const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (base + k < n) ? in[base + k] : 0u;
+    const uint32_t local = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = local;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wt[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0, all = 0;
+    for (int i = 0; i < 32; i++) {
+        if (i < w) woff += wt[i];
+        all += wt[i];
+    }
+    uint32_t run = woff + incl - local;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = all;
+}
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t *__restrict__ out, uint32_t n, const uint32_t *__restrict__ block_offs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_offs[i / SCAN_BLOCK];
+}
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total, also as 64 bit in *total). scratch: 2 * (n / SCAN_BLOCK + 2) words.
+static void scan_counts(cudaStream_t st, const uint32_t *in, uint32_t n, uint32_t *out, unsigned long long *total, uint32_t *scratch,
+                        uint64_t *launches) {
+    if (n <= 4 * SCAN_BLOCK || scratch == nullptr) {
+        k_scan_u32<<<1, 1024, 0, st>>>(in, n, out, total);
+        *launches += 1;
+        return;
+    }
+    const uint32_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;   // <= 2^20 blocks for n < 2^32; the sums' own scan stays single-CTA
+    uint32_t *sums = scratch, *offs = scratch + nb + 1;
+    k_scan_blocks<<<nb, 1024, 0, st>>>(in, n, out, sums);
+    k_scan_u32<<<1, 1024, 0, st>>>(sums, nb, offs, total);
+    k_scan_add<<<(n + 1023) / 1024, 1024, 0, st>>>(out, n, offs);
+    cudaMemcpyAsync(out + n, offs + nb, 4, cudaMemcpyDeviceToDevice, st);   // out[n] = total (fits 32 bits or the caller rejects it)
+    *launches += 3;
 }
 
 static uint32_t next_pow2(uint32_t v) {
@@ -440,6 +496,33 @@ static int tree_alloc(vb_ctx *ctx, uint32_t n, vb_tree **out) {
 using namespace vb;
 
 namespace vb {
+// The same without any host synchronisation: the hit array has room for `cap` entries (hits beyond it are dropped, the
+// offsets stay exact) and the total is left in WS_MISC[0] (64-bit) for the caller to read when it synchronises anyway.
+int kd_radius_ws_async(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint32_t cap) {
+    vb_ctx *ctx = t->ctx;
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_OFFS, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT0, (size_t)(nq + 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT1, (size_t)(cap ? cap : 1) * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_MISC, 64))) return rc;
+    uint32_t *counts = ctx->ws[WS_OFFS].as<uint32_t>();
+    uint32_t *offs = ctx->ws[WS_OUT0].as<uint32_t>();
+    unsigned long long *total_d = ctx->ws[WS_MISC].as<unsigned long long>();
+    ctx->prof_begin("kd_radius");
+    if (nq)
+        k_kd_radius<false><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q_d, nq, radius,
+                                                                                      counts, nullptr, nullptr);
+    if ((rc = ctx->ws_ensure(WS_SCAN2, (size_t)2 * (nq / SCAN_BLOCK + 3) * 4))) return rc;
+    scan_counts(ctx->stream, counts, nq, offs, total_d, ctx->ws[WS_SCAN2].as<uint32_t>(), &ctx->launches);
+    if (nq)
+        k_kd_radius<true><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q_d, nq, radius,
+                                                                                     nullptr, offs, ctx->ws[WS_OUT1].as<uint32_t>(), cap);
+    ctx->prof_end("kd_radius");
+    ctx->launches += nq ? 2 : 0;
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
 // Internal CSR radius search for callers inside the library (search by projection): offsets land in WS_OUT0
 // ([nq+1]), hit indices (original point indices, DFS pre-order per query) in WS_OUT1.
 int kd_radius_ws(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint64_t *total_out) {
@@ -455,8 +538,9 @@ int kd_radius_ws(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint6
     if (nq)
         k_kd_radius<false><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q_d, nq, radius,
                                                                                       counts, nullptr, nullptr);
-    k_scan_u32<<<1, 1024, 0, ctx->stream>>>(counts, nq, offs, total_d);
-    ctx->launches += nq ? 2 : 1;
+    if ((rc = ctx->ws_ensure(WS_SCAN2, (size_t)2 * (nq / SCAN_BLOCK + 3) * 4))) return rc;
+    scan_counts(ctx->stream, counts, nq, offs, total_d, ctx->ws[WS_SCAN2].as<uint32_t>(), &ctx->launches);
+    ctx->launches += nq ? 1 : 0;
     VB_CUDA(cudaGetLastError());
     unsigned long long total = 0;
     VB_CUDA(cudaMemcpyAsync(&total, total_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -655,8 +739,9 @@ int vb_kdtree_radius_d(vb_tree *t, const float *q_d, uint32_t nq, float radius, 
     if (nq)
         k_kd_radius<false><<<div_up(nq, KD_Q_THREADS), KD_Q_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n, q2, nq, radius,
                                                                                       counts, nullptr, nullptr);
-    k_scan_u32<<<1, 1024, 0, ctx->stream>>>(counts, nq, out_offsets_d, total_d);
-    ctx->launches += nq ? 2 : 1;
+    if ((rc = ctx->ws_ensure(WS_SCAN2, (size_t)2 * (nq / SCAN_BLOCK + 3) * 4))) return rc;
+    scan_counts(ctx->stream, counts, nq, out_offsets_d, total_d, ctx->ws[WS_SCAN2].as<uint32_t>(), &ctx->launches);
+    ctx->launches += nq ? 1 : 0;
     VB_CUDA(cudaGetLastError());
     unsigned long long total = 0;
     VB_CUDA(cudaMemcpyAsync(&total, total_d, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -23,6 +23,7 @@
 //                   Repeated until a round changes no owner (owners only ever decrease): then every
 //                   proposer holds its candidate, which is exactly the reference's outcome.
 //   k_sbp_finish    assign[i] / map_point_ids[idx] and the claim count.
+#include <algorithm>
 #include <climits>
 
 #include "common.cuh"
@@ -30,6 +31,7 @@
 namespace vb {
 
 int kd_radius_ws(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint64_t *total_out);
+int kd_radius_ws_async(vb_tree *t, const float2 *q_d, uint32_t nq, float radius, uint32_t cap);
 
 struct Cam34 {
     float c[12];
@@ -68,14 +70,14 @@ __global__ void __launch_bounds__(256) k_sbp_project(const float4 *__restrict__ 
 
 template <int W>
 __global__ void __launch_bounds__(128) k_sbp_filter(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ cand,
-                                                    uint32_t n, const uint32_t *__restrict__ desc,
+                                                    uint32_t cap, uint32_t n, const uint32_t *__restrict__ desc,
                                                     const int32_t *__restrict__ ids, const uint32_t *__restrict__ obs_off,
                                                     const uint32_t *__restrict__ obs, uint32_t thr,
                                                     uint8_t *__restrict__ accept) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t o0 = obs_off[i], o1 = obs_off[i + 1];
-    for (uint32_t c = offs[i]; c < offs[i + 1]; c++) {
+    for (uint32_t c = offs[i]; c < offs[i + 1] && c < cap; c++) {
         const uint32_t idx = cand[c];
         uint8_t ok = 0;
         if (ids[idx] < 0) {   // :151 — free when the search starts; claims made during it are the rounds' business
@@ -110,13 +112,63 @@ __global__ void __launch_bounds__(256) k_sbp_round(const uint32_t *__restrict__ 
     }
 }
 
+// Every round of the deferred acceptance in ONE launch: a grid of co-resident CTAs (grid-stride over the map points) with
+// a sense-reversing barrier in global memory between rounds, until a round lowers no owner. The host is not involved:
+// vb_search_by_projection used to synchronise once per round (0.44 ms around 0.14 ms of device work). Owners are read with
+// ld.cg (they change under atomicMin in L2); the three `changed` flags rotate so that the flag a slow CTA still reads is
+// never the one a fast CTA clears for the round after next.
+__device__ __forceinline__ void sbp_grid_barrier(unsigned int *bar, unsigned int nblocks, unsigned int &sense) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sense ^= 1u;
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == nblocks - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int *>(&bar[1]) = sense;
+        } else {
+            while (*reinterpret_cast<volatile unsigned int *>(&bar[1]) != sense) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_sbp_converge(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ cand,
+                                                      const uint8_t *__restrict__ accept, uint32_t cap, uint32_t n,
+                                                      uint32_t *__restrict__ cur, int32_t *owner, unsigned int *flags /* [3] changed, [3..4] barrier, [5] rounds */) {
+    unsigned int sense = 0;
+    for (uint32_t round = 0;; round++) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned int *>(&flags[(round + 1) % 3]) = 0u;
+        bool any = false;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            uint32_t c = cur[i];
+            uint32_t end = offs[i + 1];
+            if (end > cap) end = cap;
+            while (c < end && (!accept[c] || __ldcg(owner + cand[c]) < (int32_t)i)) c++;
+            cur[i] = c;
+            if (c < end) {
+                const int32_t old = atomicMin(owner + cand[c], (int32_t)i);
+                if (old > (int32_t)i) any = true;
+            }
+        }
+        if (any) *reinterpret_cast<volatile unsigned int *>(&flags[round % 3]) = 1u;
+        sbp_grid_barrier(flags + 3, gridDim.x, sense);
+        const unsigned int changed = *reinterpret_cast<volatile unsigned int *>(&flags[round % 3]);
+        if (!changed || round > n) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) flags[5] = round + 1u;
+            return;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sbp_finish(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ cand,
-                                                    uint32_t n, const uint32_t *__restrict__ cur, int32_t *__restrict__ assign,
+                                                    uint32_t cap, uint32_t n, const uint32_t *__restrict__ cur, int32_t *__restrict__ assign,
                                                     int32_t *__restrict__ ids, uint32_t *__restrict__ count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = cur[i];
-    if (c < offs[i + 1]) {
+    if (c < min(offs[i + 1], cap)) {
         const uint32_t idx = cand[c];
         assign[i] = (int32_t)idx;
         ids[idx] = (int32_t)i;   // :154 — one owner per keypoint by construction
@@ -163,7 +215,7 @@ int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points,
     if ((rc = ctx->ws_ensure(WS_SBP_IDS, (size_t)(k ? k : 1) * 4))) return rc;
     if ((rc = ctx->ws_ensure(WS_SBP_OBSOFF, (size_t)(n + 1) * 4))) return rc;
     if ((rc = ctx->ws_ensure(WS_SBP_OBS, (size_t)(nobs ? nobs : 1) * bytes))) return rc;
-    if ((rc = ctx->ws_ensure(WS_SBP_CUR, (size_t)n * 4 + 16))) return rc;
+    if ((rc = ctx->ws_ensure(WS_SBP_CUR, (size_t)n * 4 + 32))) return rc;
     if ((rc = ctx->ws_ensure(WS_SBP_OWNER, (size_t)(k ? k : 1) * 4))) return rc;
     if ((rc = ctx->ws_ensure(WS_SBP_ASSIGN, (size_t)n * 4))) return rc;
     cudaStream_t st = ctx->stream;
@@ -176,7 +228,7 @@ int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points,
     uint32_t *obsoff_d = ctx->ws[WS_SBP_OBSOFF].as<uint32_t>();
     uint32_t *obs_d = ctx->ws[WS_SBP_OBS].as<uint32_t>();
     uint32_t *cur_d = ctx->ws[WS_SBP_CUR].as<uint32_t>();
-    uint32_t *flags_d = cur_d + n;   // [0] changed, [1] claim count
+    uint32_t *flags_d = cur_d + n;   // [0..2] changed (rotating), [3..4] grid barrier, [5] rounds run, [6] claim count
     int32_t *owner_d = ctx->ws[WS_SBP_OWNER].as<int32_t>();
     int32_t *assign_d = ctx->ws[WS_SBP_ASSIGN].as<int32_t>();
     VB_CUDA(cudaMemcpyAsync(X_d, map_points, (size_t)n * 16, cudaMemcpyHostToDevice, st));
@@ -186,50 +238,57 @@ int vb_search_by_projection(vb_ctx *ctx, vb_tree *tree, const float *map_points,
     if (nobs) VB_CUDA(cudaMemcpyAsync(obs_d, obs_desc, (size_t)nobs * bytes, cudaMemcpyHostToDevice, st));
     Cam34 cam;
     memcpy(cam.c, camera, sizeof(cam.c));
-    ctx->prof_begin("sbp");
-    k_sbp_project<<<div_up(n, 256), 256, 0, st>>>(X_d, n, cam, (float)width, (float)height, n < 100 ? 1 : 0, q_d, proj_d, inview_d);
-    ctx->launches++;
+    // No host synchronisation between the upload and the download: the candidate array is sized for 16 hits per map point
+    // (or whatever an earlier call needed) and the whole pass is repeated with the exact size in the rare case that was
+    // not enough — the total is only known once the results are back.
+    static_assert(sizeof(unsigned long long) == 8, "");
+    uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)n * 16, ctx->sbp_cap_hint), 0xfffffff0ull);
     uint64_t total = 0;
-    if ((rc = kd_radius_ws(tree, q_d, n, radius, &total))) return rc;
-    const uint32_t *offs_d = ctx->ws[WS_OUT0].as<uint32_t>();
-    const uint32_t *cand_d = ctx->ws[WS_OUT1].as<uint32_t>();
-    if ((rc = ctx->ws_ensure(WS_SBP_ACC, (size_t)(total ? total : 1)))) return rc;
-    uint8_t *acc_d = ctx->ws[WS_SBP_ACC].as<uint8_t>();
-    if (total) {
+    for (int attempt = 0; attempt < 2; attempt++) {
+        ctx->prof_begin("sbp");
+        k_sbp_project<<<div_up(n, 256), 256, 0, st>>>(X_d, n, cam, (float)width, (float)height, n < 100 ? 1 : 0, q_d, proj_d, inview_d);
+        ctx->launches++;
+        if ((rc = kd_radius_ws_async(tree, q_d, n, radius, cap))) return rc;
+        const uint32_t *offs_d = ctx->ws[WS_OUT0].as<uint32_t>();
+        const uint32_t *cand_d = ctx->ws[WS_OUT1].as<uint32_t>();
+        if ((rc = ctx->ws_ensure(WS_SBP_ACC, (size_t)cap))) return rc;
+        uint8_t *acc_d = ctx->ws[WS_SBP_ACC].as<uint8_t>();
         switch (bytes / 4) {
-            case 4: k_sbp_filter<4><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
-            case 8: k_sbp_filter<8><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
-            default: k_sbp_filter<16><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
+            case 4: k_sbp_filter<4><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, cap, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
+            case 8: k_sbp_filter<8><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, cap, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
+            default: k_sbp_filter<16><<<div_up(n, 128), 128, 0, st>>>(offs_d, cand_d, cap, n, desc_d, ids_d, obsoff_d, obs_d, dist_threshold, acc_d); break;
         }
-        ctx->launches++;
+        if (k) k_fill_i32<<<div_up(k, 256), 256, 0, st>>>(owner_d, k, INT_MAX);
+        k_sbp_init_cur<<<div_up(n, 256), 256, 0, st>>>(offs_d, n, cur_d);
+        VB_CUDA(cudaMemsetAsync(flags_d, 0, 32, st));
+        int per_sm = 0;
+        VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sbp_converge, 256, 0));
+        const uint32_t resident = (uint32_t)(per_sm < 1 ? 1 : per_sm) * (uint32_t)ctx->sm_count;   // the barrier needs co-residency
+        const uint32_t grid = std::min(div_up(n, 256), resident);
+        k_sbp_converge<<<grid, 256, 0, st>>>(offs_d, cand_d, acc_d, cap, n, cur_d, owner_d, flags_d);
+        k_sbp_finish<<<div_up(n, 256), 256, 0, st>>>(offs_d, cand_d, cap, n, cur_d, assign_d, ids_d, flags_d + 6);
+        ctx->launches += 5;
+        ctx->prof_end("sbp");
+        VB_CUDA(cudaGetLastError());
+        VB_CUDA(cudaMemcpyAsync(&total, ctx->ws[WS_MISC].p, 8, cudaMemcpyDeviceToHost, st));
+        if (attempt == 0 && k) {   // keep the caller's ids intact until the pass is known to be complete
+            VB_CUDA(cudaStreamSynchronize(st));
+            if (total > cap) {
+                VB_REQUIRE(total <= 0xfffffff0ull, VB_ERR_CAPACITY, "radius result too large for 32-bit CSR offsets");
+                cap = (uint32_t)total;
+                ctx->sbp_cap_hint = total;
+                VB_CUDA(cudaMemcpyAsync(ids_d, map_point_ids, (size_t)k * 4, cudaMemcpyHostToDevice, st));   // finish wrote claims into it
+                continue;
+            }
+        }
+        break;
     }
-    if (k) k_fill_i32<<<div_up(k, 256), 256, 0, st>>>(owner_d, k, INT_MAX);
-    k_sbp_init_cur<<<div_up(n, 256), 256, 0, st>>>(offs_d, n, cur_d);
-    VB_CUDA(cudaMemsetAsync(flags_d, 0, 8, st));
-    ctx->launches += 2;
-    uint32_t rounds = 0;
-    for (;;) {
-        uint32_t changed = 0;
-        // one round per host check: a round that lowers no owner is the fixed point
-        VB_CUDA(cudaMemsetAsync(flags_d, 0, 4, st));
-        k_sbp_round<<<div_up(n, 256), 256, 0, st>>>(offs_d, cand_d, acc_d, n, cur_d, owner_d, flags_d);
-        ctx->launches++;
-        VB_CUDA(cudaMemcpyAsync(&changed, flags_d, 4, cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
-        rounds++;
-        if (!changed) break;
-        VB_REQUIRE(rounds <= n + 1, VB_ERR_CUDA, "search by projection did not converge");
-    }
-    k_sbp_finish<<<div_up(n, 256), 256, 0, st>>>(offs_d, cand_d, n, cur_d, assign_d, ids_d, flags_d + 1);
-    ctx->launches++;
-    ctx->prof_end("sbp");
-    VB_CUDA(cudaGetLastError());
     uint32_t claimed = 0;
     VB_CUDA(cudaMemcpyAsync(assign, assign_d, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (k) VB_CUDA(cudaMemcpyAsync(map_point_ids, ids_d, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
     if (proj_xy) VB_CUDA(cudaMemcpyAsync(proj_xy, proj_d, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (in_view) VB_CUDA(cudaMemcpyAsync(in_view, inview_d, (size_t)n, cudaMemcpyDeviceToHost, st));
-    VB_CUDA(cudaMemcpyAsync(&claimed, flags_d + 1, 4, cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaMemcpyAsync(&claimed, flags_d + 6, 4, cudaMemcpyDeviceToHost, st));
     VB_CUDA(cudaStreamSynchronize(st));
     if (n_claimed) *n_claimed = claimed;
     return VB_OK;

@@ -12,7 +12,9 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libvslam_b200.so")
+# VB_LIB_PATH: tools/ may point the binding at an out-of-tree build of the same sources (e.g. a TUNING=1 build with the
+# timing-only options compiled in); tests and bench.py always use the in-tree product build.
+LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(PKG_DIR, "lib", "libvslam_b200.so")
 
 VB_OK, VB_ERR_INVALID, VB_ERR_CUDA, VB_ERR_TOO_FEW, VB_ERR_CAPACITY, VB_ERR_NO_MODEL = range(6)
 
