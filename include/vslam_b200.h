@@ -103,6 +103,15 @@ int vb_kdtree_nearest(vb_tree *tree, const float *q_xy, uint32_t nq, float max_d
                       int32_t *out_idx, float *out_d2);
 int vb_kdtree_nearest_d(vb_tree *tree, const float *q_xy_d, uint32_t nq, float max_d2, float *out_pt_d,
                         int32_t *out_idx_d, float *out_d2_d);
+/* k nearest neighbours per query, 1 <= k <= 32 — the north star's "kNN". The reference has no behaviour to match here: its
+ * k_nearest declarations are commented out (include/KDTree.h:39-42, 74-77). Defined as the direct generalisation of `nearest`
+ * (src/KDTree.cpp:45-71): same visiting order, the strict `<` tests (:64, :68) compare against the k-th best squared distance
+ * so far (max_d2 until k candidates exist), equidistant points rank in visiting order. out_idx / out_d2 are [nq][k], ascending;
+ * unused slots hold -1 / max_d2; out_count[nq] (optional) = how many were found. k = 1 equals vb_kdtree_nearest. */
+int vb_kdtree_knn(vb_tree *tree, const float *q_xy, uint32_t nq, uint32_t k, float max_d2, int32_t *out_idx, float *out_d2,
+                  uint32_t *out_count);
+int vb_kdtree_knn_d(vb_tree *tree, const float *q_xy_d, uint32_t nq, uint32_t k, float max_d2, int32_t *out_idx_d,
+                    float *out_d2_d, uint32_t *out_count_d);
 /* Radius search for nq queries: all points with dist^2 < r^2 (strict, :91) in DFS pre-order, as CSR.
  * out_offsets[nq+1]; out_idx[cap] original indices. *out_total receives the total hit count; if it
  * exceeds cap the call returns VB_ERR_CAPACITY after filling out_offsets (retry with a larger buffer). */

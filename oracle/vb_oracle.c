@@ -619,6 +619,56 @@ int vbo_kdtree_nearest(const float *pts, const int32_t *pre_idx, int n, float qx
     return s.best_slot;
 }
 
+/* k nearest neighbours (k > 1). The reference only has commented-out declarations for this (include/KDTree.h:39-42,
+ * 74-77), so the behaviour is DEFINED here as the direct generalisation of `nearest` (src/KDTree.cpp:45-71): the same
+ * visiting order (near child, node, far child), the bound of the strict `<` tests (:64, :68) is the k-th best squared
+ * distance so far (max_distance_sq until k candidates exist), and a candidate goes into the ascending list BEHIND entries
+ * of equal distance — so among equidistant points the first visited wins, exactly as for k = 1. k = 1 is vbo_kdtree_nearest. */
+typedef struct {
+    const float *pts;
+    const int32_t *pre;
+    float qx, qy, max_d2;
+    int k, cnt;
+    int32_t *slot;
+    float *d2;
+} kd_knn;
+
+static void kd_knn_rec(kd_knn *s, int slot, int len, int axis) {
+    if (len <= 0) return;
+    const float *pt = s->pts + 2 * (size_t)s->pre[slot];
+    const float q_ax = axis ? s->qy : s->qx;
+    const float split = q_ax - pt[axis];
+    const int llen = len / 2, rlen = len - llen - 1;
+    const int lslot = slot + 1, rslot = slot + 1 + llen;
+    int far_slot, far_len;
+    if (split < 0) {
+        kd_knn_rec(s, lslot, llen, 1 - axis);
+        far_slot = rslot; far_len = rlen;
+    } else {
+        kd_knn_rec(s, rslot, rlen, 1 - axis);
+        far_slot = lslot; far_len = llen;
+    }
+    float dx = pt[0] - s->qx, dy = pt[1] - s->qy;
+    float d2 = dx * dx + dy * dy;
+    float bound = (s->cnt < s->k) ? s->max_d2 : s->d2[s->k - 1];
+    if (d2 < bound) {
+        int j = (s->cnt < s->k) ? s->cnt : s->k - 1;   /* position being filled: a new tail, or the evicted k-th */
+        while (j > 0 && s->d2[j - 1] > d2) { s->d2[j] = s->d2[j - 1]; s->slot[j] = s->slot[j - 1]; j--; }
+        s->d2[j] = d2; s->slot[j] = slot;
+        if (s->cnt < s->k) s->cnt++;
+    }
+    bound = (s->cnt < s->k) ? s->max_d2 : s->d2[s->k - 1];
+    if (split * split < bound) kd_knn_rec(s, far_slot, far_len, 1 - axis);
+}
+
+int vbo_kdtree_knn(const float *pts, const int32_t *pre_idx, int n, float qx, float qy, int k, float max_d2,
+                   int32_t *out_slot, float *out_d2) {
+    kd_knn s = {pts, pre_idx, qx, qy, max_d2, k, 0, out_slot, out_d2};
+    if (k <= 0) return 0;
+    kd_knn_rec(&s, 0, n, 0);
+    return s.cnt;
+}
+
 typedef struct {
     const float *pts;
     const int32_t *pre;

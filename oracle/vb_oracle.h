@@ -115,6 +115,11 @@ int vbo_kdtree_nearest(const float *pts, const int32_t *pre_idx, int n, float qx
                        float *out_d2);
 /* radius_search (:73-101, :145-171): writes matching point indices in DFS pre-order; returns count
  * (may exceed cap; only cap entries are written). */
+/* k > 1 nearest neighbours: build-defined generalisation of `nearest` (no reference behaviour exists: the declarations at
+ * include/KDTree.h:39-42,74-77 are commented out). Ascending by squared distance, first visited first among equals.
+ * out_slot / out_d2 have room for k entries; returns how many were found (< k when fewer points lie within max_d2). */
+int vbo_kdtree_knn(const float *pts, const int32_t *pre_idx, int n, float qx, float qy, int k, float max_d2,
+                   int32_t *out_slot, float *out_d2);
 int vbo_kdtree_radius(const float *pts, const int32_t *pre_idx, int n, float qx, float qy, float radius,
                       int32_t *out_idx, int cap);
 

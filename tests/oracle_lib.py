@@ -70,6 +70,8 @@ class Oracle:
         L.vbo_kdtree_height.restype = C.c_int
         L.vbo_kdtree_nearest.restype = C.c_int
         L.vbo_kdtree_nearest.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+        L.vbo_kdtree_knn.restype = C.c_int
+        L.vbo_kdtree_knn.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _i32p, _f32p]
         L.vbo_kdtree_radius.restype = C.c_int
         L.vbo_kdtree_radius.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_float, C.c_float, _i32p, C.c_int]
         L.vbo_orb_distance.restype = C.c_uint32
@@ -260,6 +262,12 @@ class Oracle:
         d2 = C.c_float()
         slot = self.lib.vbo_kdtree_nearest(pts, pre, len(pts), q[0], q[1], max_d2, C.byref(d2))
         return slot, np.float32(d2.value)
+
+    def kdtree_knn(self, pts, pre, q, k, max_d2=np.inf):
+        """-> (pre-order slots [found], squared distances [found])."""
+        slot, d2 = np.zeros(max(k, 1), np.int32), np.zeros(max(k, 1), np.float32)
+        c = self.lib.vbo_kdtree_knn(pts, pre, len(pts), q[0], q[1], k, max_d2, slot, d2)
+        return slot[:c].copy(), d2[:c].copy()
 
     def kdtree_radius(self, pts, pre, q, r, cap=None):
         cap = cap or len(pts)

@@ -367,7 +367,7 @@ def test_pairs_run_degenerate_pair_in_batch(ctx, oracle):
 
 
 # ---------------------------------------------------------------- KD-tree
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 100, 1023, 1024, 1025, 5000, 7000, 20000])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 100, 1023, 1024, 1025, 5000, 6144, 6145, 7000, 12289, 20000, 100000])
 def test_kdtree_build_bit_exact(ctx, oracle, n):
     pts = synth.frame_pair(max(n, 8), n + 1)["p1"][:n].copy()
     t = ctx.kdtree_build(pts)
@@ -379,15 +379,18 @@ def test_kdtree_build_bit_exact(ctx, oracle, n):
     t.free()
 
 
-def test_kdtree_build_with_ties(ctx, oracle):
-    """Integer grid coordinates as in the reference's own test (tests/test_kdtree.cpp:39-45): massive ties.
-    The documented tie order (coordinate, then original index) must match the oracle's."""
-    rng = np.random.default_rng(0)
-    pts = rng.integers(0, 100, (2700, 2)).astype(np.float32)
+@pytest.mark.parametrize("n", [2700, 9000, 30000])
+def test_kdtree_build_with_ties(ctx, oracle, n):
+    """Integer grid coordinates as in the reference's own test (tests/test_kdtree.cpp:39-45): massive ties. The documented
+    tie order (coordinate, then original index) must match the oracle's — in the one-CTA build and through the top-down
+    levels of a large tree (radix-selected medians inside runs of equal coordinates, stable partitions)."""
+    rng = np.random.default_rng(n)
+    pts = rng.integers(0, 100, (n, 2)).astype(np.float32)
+    pts[: n // 10] = pts[0]                                   # and one long run of identical points
     t = ctx.kdtree_build(pts)
     idx, _ = t.export()
     assert np.array_equal(idx.astype(np.int32), oracle.kdtree_build(pts))
-    assert sorted(idx.tolist()) == list(range(2700))
+    assert sorted(idx.tolist()) == list(range(n))
 
 
 @pytest.mark.parametrize("n", [1, 5, 3000, 5000, 20000])
@@ -435,6 +438,37 @@ def test_kdtree_nearest_lane_mappings_agree(ctx, oracle, lanes):
     for i in range(0, 3000, 60):
         slot, od2 = oracle.kdtree_nearest(pts, pre, q[i])
         assert idx2[i] == pre[slot] and d2[i] == od2
+    t.free()
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 8), (3000, 1), (3000, 2), (5000, 8), (20000, 32)])
+def test_kdtree_knn_bit_exact(ctx, oracle, n, k):
+    """k nearest neighbours (build-defined generalisation of `nearest`, src/KDTree.cpp:45-71; the reference's k_nearest is a
+    commented-out declaration): indices, distances and counts equal the oracle's; k = 1 equals vb_kdtree_nearest; against
+    brute force the distance lists agree; a finite max_d2 truncates the list."""
+    rng = np.random.default_rng(n + k)
+    pts = synth.frame_pair(max(n, 8), n + 5)["p1"][:n].copy()
+    pre = oracle.kdtree_build(pts)
+    t = ctx.kdtree_build(pts)
+    nq = 400
+    q = np.ascontiguousarray(pts[rng.integers(0, n, nq)] + rng.uniform(-4, 4, (nq, 2)), np.float32)
+    q[:10] = pts[rng.integers(0, n, 10)]
+    idx, d2, cnt = t.knn(q, k)
+    for i in range(nq):
+        slot, od2 = oracle.kdtree_knn(pts, pre, q[i], k)
+        assert cnt[i] == len(slot) == min(k, n)
+        assert np.array_equal(idx[i, :cnt[i]], pre[slot]) and np.array_equal(bits(d2[i, :cnt[i]]), bits(od2))
+        assert (idx[i, cnt[i]:] == -1).all()
+    dd = ((pts[None, :, :].astype(np.float32) - q[:50, None, :]) ** 2)
+    bf = np.sort((dd[..., 0] + dd[..., 1]).astype(np.float32), axis=1)[:, :min(k, n)]
+    assert np.allclose(d2[:50, :min(k, n)], bf, rtol=1e-6)
+    if k == 1:
+        _, i1, e1 = t.nearest(q)
+        assert np.array_equal(i1, idx[:, 0]) and np.array_equal(bits(e1), bits(d2[:, 0]))
+    idx2, d22, cnt2 = t.knn(q, k, 9.0)                                  # bounded: only points within 3 px
+    for i in range(0, nq, 7):
+        slot, od2 = oracle.kdtree_knn(pts, pre, q[i], k, 9.0)
+        assert cnt2[i] == len(slot) and np.array_equal(idx2[i, :cnt2[i]], pre[slot]) and (d22[i, :cnt2[i]] < 9.0).all()
     t.free()
 
 

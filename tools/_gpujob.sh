@@ -1,6 +1,4 @@
-export VB_LIB_PATH=$PWD/vslam_b200/lib_tuning/libvslam_b200.so
-for o in "tc_drain=1" "tc_drain=1,pairs_split=1" "tc_drain=0,pairs_split=1" "tc_drain=3,pairs_split=1"; do
-  VB_OPTIONS=$o python bench.py --quick --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$o', 'ms_per_step', round(d['ms_per_step'],3), 'value', round(d['value']), 'e2e', round(d['e2e']['value']))"
-done > gpurun_out/r2g_split.log 2>&1
-cat gpurun_out/r2g_split.log
+python -m pytest tests -x -q -m gpu -k "kdtree or projection or adapter" 2>&1 | tail -15 > gpurun_out/r2i_kd_tests.log; cat gpurun_out/r2i_kd_tests.log
+NQ=1048576 python tools/kd_profile.py > gpurun_out/r2i_kd.json 2> gpurun_out/r2i_kd.err; tail -3 gpurun_out/r2i_kd.err; python -c "
+import json; d=json.load(open('gpurun_out/r2i_kd.json'))
+for r in d['throughput']: print(r['tree_points'], 'build_ms', r['build_ms_single_tree'], 'nearest_ms', r['nearest']['ms'], 'radius_ms', r['radius2']['ms'])"

@@ -90,7 +90,7 @@ enum WsSlot {
     WS_P1 = 0, WS_P2, WS_MATCHES, WS_CORR, WS_M, WS_SETS, WS_RAW, WS_FALL, WS_PART_CNT, WS_PART_SUM, WS_CNT, WS_SCORE,
     WS_RESULT, WS_MASK, WS_OUTMATCH, WS_D1, WS_D2, WS_KNN_PART, WS_KNN, WS_TENT, WS_FLAGS, WS_Q, WS_OUT0, WS_OUT1,
     WS_OUT2, WS_OFFS, WS_SCAN, WS_PTS, WS_DESC, WS_SEEDS, WS_MISC, WS_L2A, WS_L2B, WS_L2C, WS_L2N, WS_L2M, WS_L2H, WS_EXP, WS_SBP_X, WS_SBP_Q, WS_SBP_DESC, WS_SBP_IDS, WS_SBP_OBSOFF,
-    WS_SBP_OBS, WS_SBP_ACC, WS_SBP_CUR, WS_SBP_OWNER, WS_SBP_ASSIGN, WS_BOUNDS, WS_TIED, WS_PRUNE, WS_PRUNE_STATS, WS_ALIVE, WS_BQ_ITEMS, WS_BQ_VALID, WS_BQ_CTL, WS_BQ_ORDER, WS_FOLD_CNT, WS_FOLD_SUM, WS_SCAN2, WS_COUNT
+    WS_SBP_OBS, WS_SBP_ACC, WS_SBP_CUR, WS_SBP_OWNER, WS_SBP_ASSIGN, WS_BOUNDS, WS_TIED, WS_PRUNE, WS_PRUNE_STATS, WS_ALIVE, WS_BQ_ITEMS, WS_BQ_VALID, WS_BQ_CTL, WS_BQ_ORDER, WS_FOLD_CNT, WS_FOLD_SUM, WS_SCAN2, WS_KD_TOP, WS_COUNT
 };
 
 struct ProfEntry {
@@ -121,6 +121,7 @@ struct vb_ctx {
     vb::DevBuf ws[vb::WS_COUNT];
     vb::PinBuf pin[4];
     uint64_t launches = 0;
+    std::vector<uint4> kd_segs_host;   // segment table of the last top-down k-d tree build (source of an asynchronous upload)
     uint64_t sbp_cap_hint = 0;     // largest candidate count a search-by-projection call has needed so far
     uint32_t func_attr_done = 0;   // per-context (hence per-device) bits: large-smem attribute set for kernel i
     bool profile = false;

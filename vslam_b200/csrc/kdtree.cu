@@ -20,6 +20,9 @@
 // Queries (k_kd_nearest, k_kd_radius): one thread per query, explicit stack in shared memory laid out
 // [depth][thread] (bank-conflict free). The visiting order is exactly the reference's recursion, so
 // equidistant nearest-neighbour ties and the pre-order of radius results come out identical.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace vb {
@@ -115,13 +118,26 @@ struct KdBuildArgs {
     size_t ws_stride;
     int lists_in_smem;       // working arrays in dynamic shared memory
     int keys_mode;           // 0: both key arrays in smem, 1: one at a time in smem, 2: global
+    // sub-tree mode (top-down build of a large tree): CTA b builds the sub-tree of segment segs[b] = (start, len, slot):
+    // its points are pts[start .. start + len), its nodes go to out[slot ...], its first level splits on axis0, and the
+    // original point index of local point i is ord[start + i]
+    const uint4 *segs;
+    const uint32_t *ord;
+    uint32_t axis0;
 };
 
 __global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint64_t warp_tot[KD_BUILD_THREADS / 32];
-    const uint32_t n = a.n, npad = a.npad, tid = threadIdx.x;
-    const float2 *pts = a.pts + (size_t)blockIdx.x * a.pts_stride;
+    const uint32_t tid = threadIdx.x;
+    uint32_t n = a.n, npad = a.npad, seg_start = 0, seg_slot = 0;
+    if (a.segs) {
+        const uint4 sg = a.segs[blockIdx.x];
+        seg_start = sg.x; n = sg.y; seg_slot = sg.z;
+        npad = 1;
+        while (npad < n) npad <<= 1;
+    }
+    const float2 *pts = a.segs ? a.pts + seg_start : a.pts + (size_t)blockIdx.x * a.pts_stride;
     uint8_t *gws = a.ws ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr;
 
     // ---- carve the working arrays -----------------------------------------------------------
@@ -188,16 +204,18 @@ __global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
     for (uint32_t p = tid; p < n; p += blockDim.x) { segL[p] = 0; segR[p] = n; segB[p] = 0; }
     __syncthreads();
 
-    float *ox = a.out_x + (size_t)blockIdx.x * a.out_stride;
-    float *oy = a.out_y + (size_t)blockIdx.x * a.out_stride;
-    uint32_t *oi = a.out_idx + (size_t)blockIdx.x * a.out_stride;
+    float *ox = a.segs ? a.out_x + seg_slot : a.out_x + (size_t)blockIdx.x * a.out_stride;
+    float *oy = a.segs ? a.out_y + seg_slot : a.out_y + (size_t)blockIdx.x * a.out_stride;
+    uint32_t *oi = a.segs ? a.out_idx + seg_slot : a.out_idx + (size_t)blockIdx.x * a.out_stride;
+    const uint32_t *omap = a.segs ? a.ord + seg_start : nullptr;
 
     // ---- one pass per tree level ---------------------------------------------------------------
     uint32_t height = 0;
     for (uint32_t t = n; t > 0; t >>= 1) height++;
     for (uint32_t level = 0; level < height; level++) {
-        uint32_t *A = (level & 1) ? Ly : Lx;    // list sorted along this level's axis
-        uint32_t *Bl = (level & 1) ? Lx : Ly;   // the other list, to be partitioned
+        const uint32_t ax = (level + a.axis0) & 1u;
+        uint32_t *A = ax ? Ly : Lx;    // list sorted along this level's axis
+        uint32_t *Bl = ax ? Lx : Ly;   // the other list, to be partitioned
         // pass 1: classify every point of every live segment; medians become tree nodes
         for (uint32_t p = tid; p < n; p += blockDim.x) {
             const uint32_t l = segL[p], r = segR[p];
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
                 if (p == m) {
                     const float2 v = pts[pt];
                     const uint32_t slot = segB[p];
-                    ox[slot] = v.x; oy[slot] = v.y; oi[slot] = pt;
+                    ox[slot] = v.x; oy[slot] = v.y; oi[slot] = omap ? omap[pt] : pt;
                 }
             }
         }
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(KD_BUILD_THREADS) k_kd_build(KdBuildArgs a) {
             }
         }
         // rotate buffers: the partitioned copy becomes the current "other" list
-        if (level & 1) { uint32_t *t = Lx; Lx = spare; spare = t; }
+        if (ax) { uint32_t *t = Lx; Lx = spare; spare = t; }
         else { uint32_t *t = Ly; Ly = spare; spare = t; }
         __syncthreads();
     }
@@ -293,6 +311,62 @@ __global__ void __launch_bounds__(KD_Q_THREADS) k_kd_nearest(const float *__rest
     if (out_pt) out_pt[i] = best_slot >= 0 ? make_float2(tx[best_slot], ty[best_slot]) : make_float2(0.f, 0.f);
     if (out_idx) out_idx[i] = best_slot >= 0 ? (int32_t)tidx[best_slot] : -1;
     if (out_d2) out_d2[i] = best;
+}
+
+// k nearest neighbours, k <= KD_KNN_MAX: the traversal of k_kd_nearest with the k-th best distance as the bound and an
+// ascending candidate list per query in shared memory ([k][thread], conflict-free). Build-defined (the reference only has
+// commented-out declarations, include/KDTree.h:39-42): first visited first among equal distances, like `nearest`.
+constexpr int KD_KNN_MAX = 32;
+constexpr int KD_KNN_THREADS = 64;
+__global__ void __launch_bounds__(KD_KNN_THREADS) k_kd_knn(const float *__restrict__ tx, const float *__restrict__ ty,
+                                                           const uint32_t *__restrict__ tidx, uint32_t n,
+                                                           const float2 *__restrict__ q, uint32_t nq, uint32_t k, float max_d2,
+                                                           int32_t *__restrict__ out_idx, float *__restrict__ out_d2,
+                                                           uint32_t *__restrict__ out_cnt) {
+    __shared__ uint2 stack[KD_MAX_DEPTH][KD_KNN_THREADS];
+    __shared__ float ld2[KD_KNN_MAX][KD_KNN_THREADS];
+    __shared__ uint32_t lslot[KD_KNN_MAX][KD_KNN_THREADS];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, t = threadIdx.x;
+    if (i >= nq) return;
+    const float2 qp = q[i];
+    uint32_t cnt = 0;
+    float bound = max_d2;
+    int sp = 0;
+    if (n > 0) stack[sp++][t] = make_uint2(0u, n);
+    while (sp > 0) {
+        const uint2 f = stack[sp - 1][t];
+        const uint32_t slot = f.x, len = f.y & 0x3fffffffu, axis = (f.y >> 30) & 1u, state = f.y >> 31;
+        const float x = __ldg(tx + slot), y = __ldg(ty + slot);
+        const float split = axis ? __fsub_rn(qp.y, y) : __fsub_rn(qp.x, x);
+        const uint32_t llen = len >> 1, rlen = len - llen - 1;
+        const bool go_left = split < 0.0f;
+        if (state == 0) {
+            stack[sp - 1][t].y = f.y | 0x80000000u;
+            const uint32_t cs = go_left ? slot + 1 : slot + 1 + llen, cl = go_left ? llen : rlen;
+            if (cl > 0) { stack[sp][t] = make_uint2(cs, cl | ((axis ^ 1u) << 30)); sp++; }
+        } else {
+            sp--;
+            const float dx = __fsub_rn(x, qp.x), dy = __fsub_rn(y, qp.y);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (d2 < bound) {
+                uint32_t j = cnt < k ? cnt : k - 1;
+                while (j > 0 && ld2[j - 1][t] > d2) { ld2[j][t] = ld2[j - 1][t]; lslot[j][t] = lslot[j - 1][t]; j--; }
+                ld2[j][t] = d2; lslot[j][t] = slot;
+                if (cnt < k) cnt++;
+                bound = cnt < k ? max_d2 : ld2[k - 1][t];
+            }
+            const uint32_t cs = go_left ? slot + 1 + llen : slot + 1, cl = go_left ? rlen : llen;
+            if (cl > 0 && __fmul_rn(split, split) < bound) {
+                stack[sp][t] = make_uint2(cs, cl | ((axis ^ 1u) << 30));
+                sp++;
+            }
+        }
+    }
+    for (uint32_t j = 0; j < k; j++) {
+        out_idx[(size_t)i * k + j] = j < cnt ? (int32_t)tidx[lslot[j][t]] : -1;
+        out_d2[(size_t)i * k + j] = j < cnt ? ld2[j][t] : max_d2;
+    }
+    if (out_cnt) out_cnt[i] = cnt;
 }
 
 template <bool FILL>
@@ -428,6 +502,113 @@ static void scan_counts(cudaStream_t st, const uint32_t *in, uint32_t n, uint32_
     *launches += 3;
 }
 
+// ---- top-down levels of a LARGE tree --------------------------------------------------------------------------------
+// k_kd_build sorts a whole tree inside one CTA; past ~6 000 points its working set leaves shared memory and a single CTA
+// grinds through an HBM-resident bitonic sort (3.3 ms for 20 000 points — slower than one host core). The shape of the
+// tree does not depend on the data (the median sits at position l + len/2, src/KDTree.cpp:8), so the segments of every
+// level are known up front: the top levels are peeled off with one CTA per segment — radix-select the median of the level's
+// coordinate, emit it as the node, stably partition the segment's index list around it — until the segments fit shared
+// memory, and k_kd_build then builds all the sub-trees in one launch (sub-tree mode). Ties on the coordinate fall to the
+// lower original index, as everywhere: the index list starts ascending and every partition is stable.
+constexpr uint32_t KD_SPLIT_THREADS = 1024;
+constexpr uint32_t KD_SMEM_MAX_POINTS = 6144;
+
+__global__ void __launch_bounds__(KD_SPLIT_THREADS) k_kd_split(const float2 *__restrict__ pts, const uint32_t *__restrict__ ord_in,
+                                                               uint32_t *__restrict__ ord_out, const uint4 *__restrict__ segs,
+                                                               uint32_t axis, float *__restrict__ ox, float *__restrict__ oy,
+                                                               uint32_t *__restrict__ oi) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rank, s_less, s_pick;
+    __shared__ uint32_t wsum[32][3];
+    __shared__ uint32_t s_run[3];
+    const uint4 sg = segs[blockIdx.x];
+    const uint32_t l = sg.x, len = sg.y, slot = sg.z, tid = threadIdx.x;
+    if (len == 0) return;
+    const uint32_t k = len / 2;   // rank of the median in (coordinate, position) order; position order = original index order
+    auto coord = [&](uint32_t i) {
+        const float2 v = pts[ord_in[l + i]];
+        return float_orderable(axis ? v.y : v.x);
+    };
+    // -- radix select of the k-th smallest coordinate (4 passes of 8 bits, most significant first) --
+    if (tid == 0) { s_prefix = 0; s_rank = k; }
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 24 - 8 * pass;
+        for (uint32_t b = tid; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, himask = pass ? (0xffffffffu << (shift + 8)) : 0u;
+        for (uint32_t i = tid; i < len; i += blockDim.x) {
+            const uint32_t c = coord(i);
+            if ((c & himask) == prefix) atomicAdd(&hist[(c >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t r = s_rank, b = 0;
+            for (; b < 256; b++) {
+                if (r < hist[b]) break;
+                r -= hist[b];
+            }
+            s_prefix = prefix | (b << shift);
+            s_rank = r;
+        }
+        __syncthreads();
+    }
+    const uint32_t cstar = s_prefix;        // the median's coordinate
+    const uint32_t eq_rank = s_rank;        // ... it is the eq_rank-th (0-based, in position order) of the points with that coordinate
+    // -- stable three-way partition: [l, l + k) <- smaller, l + k <- the median, (l + k, l + len) <- larger --
+    if (tid < 3) s_run[tid] = 0;            // running counts: left, equal-to-cstar seen, right
+    __syncthreads();
+    const int lane = tid & 31, w = tid >> 5;
+    for (uint32_t i0 = 0; i0 < len; i0 += blockDim.x) {
+        const uint32_t i = i0 + tid;
+        uint32_t c = 0, id = 0;
+        int isl = 0, ise = 0, isr = 0;
+        if (i < len) {
+            id = ord_in[l + i];
+            const float2 v = pts[id];
+            c = float_orderable(axis ? v.y : v.x);
+            isl = c < cstar; ise = c == cstar; isr = c > cstar;
+        }
+        const unsigned bl = __ballot_sync(0xffffffffu, isl), be = __ballot_sync(0xffffffffu, ise), br = __ballot_sync(0xffffffffu, isr);
+        if (lane == 0) { wsum[w][0] = __popc(bl); wsum[w][1] = __popc(be); wsum[w][2] = __popc(br); }
+        __syncthreads();
+        uint32_t pl = s_run[0], pe = s_run[1], pr = s_run[2], tl = 0, te = 0, tr = 0;
+        for (int q = 0; q < 32; q++) {
+            if (q < w) { pl += wsum[q][0]; pe += wsum[q][1]; pr += wsum[q][2]; }
+            tl += wsum[q][0]; te += wsum[q][1]; tr += wsum[q][2];
+        }
+        const unsigned below = (1u << lane) - 1u;
+        pl += __popc(bl & below); pe += __popc(be & below); pr += __popc(br & below);
+        if (i < len) {
+            // equal coordinates: the first eq_rank of them (position order) are "smaller", the next one is the median
+            // number of equal-coordinate points that end up left of a given equal point = min(its equal-rank, eq_rank)
+            uint32_t dst;
+            if (isl) dst = l + pl + min(pe, eq_rank);
+            else if (ise && pe < eq_rank) dst = l + pl + pe;
+            else if (ise && pe == eq_rank) dst = l + k;
+            else if (ise) dst = l + k + 1 + pr + (pe - eq_rank - 1);
+            else dst = l + k + 1 + pr + (pe > eq_rank ? pe - eq_rank - 1 : 0);
+            ord_out[dst] = id;
+            if (ise && pe == eq_rank) {
+                const float2 v = pts[id];
+                ox[slot] = v.x; oy[slot] = v.y; oi[slot] = id;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { s_run[0] += tl; s_run[1] += te; s_run[2] += tr; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_kd_iota(uint32_t *p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void __launch_bounds__(256) k_kd_gather(const float2 *__restrict__ pts, const uint32_t *__restrict__ ord, uint32_t n,
+                                                   float2 *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pts[ord[i]];
+}
+
 static uint32_t next_pow2(uint32_t v) {
     uint32_t p = 1;
     while (p < v) p <<= 1;
@@ -435,9 +616,72 @@ static uint32_t next_pow2(uint32_t v) {
 }
 
 // Builds ntrees trees of n points each. out arrays are [ntrees][out_stride].
+// One large tree, top-down (see k_kd_split). Workspace (WS_KD_TOP): two index lists, the gathered points, the segment tables.
+static int kd_build_topdown(vb_ctx *ctx, const float2 *pts_d, uint32_t n, float *ox, float *oy, uint32_t *oi) {
+    uint32_t levels = 0;
+    while (((n >> levels) + 1) > KD_SMEM_MAX_POINTS) levels++;   // segment lengths at level L are <= ceil(n / 2^L)
+    // the segments of every level (data-independent): (start, len, pre-order slot)
+    std::vector<std::vector<uint4>> segs(levels + 1);
+    segs[0].push_back(make_uint4(0u, n, 0u, 0u));
+    for (uint32_t L = 0; L < levels; L++)
+        for (const uint4 &sg : segs[L]) {
+            const uint32_t l = sg.x, len = sg.y, slot = sg.z, k = len / 2;
+            segs[L + 1].push_back(make_uint4(l, k, slot + 1, 0u));
+            segs[L + 1].push_back(make_uint4(l + k + 1, len - k - 1, slot + 1 + k, 0u));
+        }
+    size_t nseg_total = 0;
+    for (auto &v : segs) nseg_total += v.size();
+    const size_t off_ord = 0, off_pts = (size_t)n * 8, off_segs = off_pts + (size_t)n * 8;
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_KD_TOP, off_segs + nseg_total * sizeof(uint4)))) return rc;
+    uint8_t *base = ctx->ws[WS_KD_TOP].as<uint8_t>();
+    uint32_t *ordA = reinterpret_cast<uint32_t *>(base + off_ord), *ordB = ordA + n;
+    float2 *gpts = reinterpret_cast<float2 *>(base + off_pts);
+    uint4 *segs_d = reinterpret_cast<uint4 *>(base + off_segs);
+    std::vector<uint4> &flat = ctx->kd_segs_host;   // kept alive by the context: the upload below is asynchronous
+    flat.clear();
+    std::vector<size_t> level_off;
+    for (auto &v : segs) { level_off.push_back(flat.size()); flat.insert(flat.end(), v.begin(), v.end()); }
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));   // an earlier build may still be reading the table (rare path: large trees)
+    VB_CUDA(cudaMemcpyAsync(segs_d, flat.data(), flat.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof_begin("kd_build");
+    k_kd_iota<<<div_up(n, 256), 256, 0, ctx->stream>>>(ordA, n);
+    uint32_t *cur = ordA, *nxt = ordB;
+    for (uint32_t L = 0; L < levels; L++) {
+        // a level's partitions only fill the children's ranges; the medians' own slots in the next list are never read
+        k_kd_split<<<(unsigned)segs[L].size(), KD_SPLIT_THREADS, 0, ctx->stream>>>(pts_d, cur, nxt, segs_d + level_off[L], L & 1u, ox, oy, oi);
+        std::swap(cur, nxt);
+    }
+    k_kd_gather<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts_d, cur, n, gpts);
+    KdBuildArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pts = gpts; a.n = (n >> levels) + 1; a.npad = 1;
+    while (a.npad < a.n) a.npad <<= 1;
+    a.out_x = ox; a.out_y = oy; a.out_idx = oi;
+    a.lists_in_smem = 1; a.keys_mode = 0;
+    a.segs = segs_d + level_off[levels]; a.ord = cur; a.axis0 = levels & 1u;
+    const size_t lists_bytes = (size_t)(a.n + 1) * 8 + (size_t)a.n * 24 + ((a.n + 7) / 8) * 8;
+    const size_t keys2 = (size_t)a.npad * 16;
+    const size_t smem = lists_bytes > keys2 ? lists_bytes : keys2;
+    VB_CUDA(cudaFuncSetAttribute(k_kd_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_kd_build<<<(unsigned)segs[levels].size(), KD_BUILD_THREADS, smem, ctx->stream>>>(a);
+    ctx->prof_end("kd_build");
+    ctx->launches += 3 + levels;
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
 int kd_build_launch(vb_ctx *ctx, const float2 *pts_d, size_t pts_stride, uint32_t ntrees, uint32_t n, float *ox, float *oy,
                     uint32_t *oi, size_t out_stride) {
     if (n == 0 || ntrees == 0) return VB_OK;
+    if (n > KD_SMEM_MAX_POINTS) {   // large trees: top-down, many CTAs per tree
+        for (uint32_t t = 0; t < ntrees; t++) {
+            int rc = kd_build_topdown(ctx, pts_d + (size_t)t * pts_stride, n, ox + (size_t)t * out_stride, oy + (size_t)t * out_stride,
+                                      oi + (size_t)t * out_stride);
+            if (rc) return rc;
+        }
+        return VB_OK;
+    }
     KdBuildArgs a;
     memset(&a, 0, sizeof(a));
     a.pts = pts_d; a.pts_stride = pts_stride; a.n = n; a.npad = next_pow2(n);
@@ -720,6 +964,46 @@ int vb_kdtree_nearest(vb_tree *t, const float *q, uint32_t nq, float max_d2, flo
     if (out_pt) VB_CUDA(cudaMemcpyAsync(out_pt, ctx->ws[WS_OUT0].p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_idx) VB_CUDA(cudaMemcpyAsync(out_idx, ctx->ws[WS_OUT1].p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_d2) VB_CUDA(cudaMemcpyAsync(out_d2, ctx->ws[WS_OUT2].p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VB_OK;
+}
+
+int vb_kdtree_knn_d(vb_tree *t, const float *q_d, uint32_t nq, uint32_t k, float max_d2, int32_t *out_idx_d, float *out_d2_d,
+                    uint32_t *out_count_d) {
+    VB_REQUIRE(t && out_idx_d && out_d2_d && (q_d || nq == 0), VB_ERR_INVALID, "NULL argument");
+    VB_REQUIRE(k >= 1 && k <= (uint32_t)KD_KNN_MAX, VB_ERR_INVALID, "k must be in 1..32");
+    if (nq == 0) return VB_OK;
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    ctx->prof_begin("kd_knn");
+    k_kd_knn<<<div_up(nq, KD_KNN_THREADS), KD_KNN_THREADS, 0, ctx->stream>>>(t->x, t->y, t->idx, t->n,
+                                                                            reinterpret_cast<const float2 *>(q_d), nq, k, max_d2,
+                                                                            out_idx_d, out_d2_d, out_count_d);
+    ctx->prof_end("kd_knn");
+    ctx->launches++;
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_kdtree_knn(vb_tree *t, const float *q, uint32_t nq, uint32_t k, float max_d2, int32_t *out_idx, float *out_d2,
+                  uint32_t *out_count) {
+    VB_REQUIRE(t && out_idx && out_d2 && (q || nq == 0), VB_ERR_INVALID, "NULL argument");
+    VB_REQUIRE(k >= 1 && k <= (uint32_t)KD_KNN_MAX, VB_ERR_INVALID, "k must be in 1..32");
+    if (nq == 0) return VB_OK;
+    vb_ctx *ctx = t->ctx;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->ws_ensure(WS_Q, (size_t)nq * 8))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT0, (size_t)nq * k * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT1, (size_t)nq * k * 4))) return rc;
+    if ((rc = ctx->ws_ensure(WS_OUT2, (size_t)nq * 4))) return rc;
+    VB_CUDA(cudaMemcpyAsync(ctx->ws[WS_Q].p, q, (size_t)nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vb_kdtree_knn_d(t, ctx->ws[WS_Q].as<float>(), nq, k, max_d2, ctx->ws[WS_OUT0].as<int32_t>(), ctx->ws[WS_OUT1].as<float>(),
+                              ctx->ws[WS_OUT2].as<uint32_t>())))
+        return rc;
+    VB_CUDA(cudaMemcpyAsync(out_idx, ctx->ws[WS_OUT0].p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VB_CUDA(cudaMemcpyAsync(out_d2, ctx->ws[WS_OUT1].p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_count) VB_CUDA(cudaMemcpyAsync(out_count, ctx->ws[WS_OUT2].p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     VB_CUDA(cudaStreamSynchronize(ctx->stream));
     return VB_OK;
 }

@@ -42,7 +42,7 @@ assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 60
 EXPORTS = [
     "vb_version", "vb_last_error", "vb_create", "vb_destroy", "vb_set_stream", "vb_set_option", "vb_reset_options", "vb_synchronize", "vb_launch_count",
     "vb_kdtree_build", "vb_kdtree_build_d", "vb_kdtree_build_batch_d", "vb_kdtree_free_batch", "vb_kdtree_import", "vb_kdtree_free", "vb_kdtree_size", "vb_kdtree_height", "vb_kdtree_export",
-    "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
+    "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_knn", "vb_kdtree_knn_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_fundamental_ex", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
     "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
@@ -90,6 +90,8 @@ def load_library() -> C.CDLL:
     L.vb_kdtree_export.argtypes = [vp, vp, vp]
     L.vb_kdtree_nearest.argtypes = [vp, vp, u32, f32, vp, vp, vp]
     L.vb_kdtree_nearest_d.argtypes = [vp, vp, u32, f32, vp, vp, vp]
+    L.vb_kdtree_knn.argtypes = [vp, vp, u32, u32, f32, vp, vp, vp]
+    L.vb_kdtree_knn_d.argtypes = [vp, vp, u32, u32, f32, vp, vp, vp]
     L.vb_kdtree_radius.argtypes = [vp, vp, u32, f32, vp, vp, u64, C.POINTER(u64)]
     L.vb_kdtree_radius_d.argtypes = [vp, vp, u32, f32, vp, vp, u64, C.POINTER(u64)]
     L.vb_knn2_hamming.argtypes = [vp, vp, u32, vp, u32, u32, vp, vp]
@@ -477,6 +479,13 @@ class KDTreeHandle:
         pt, idx, d2 = np.zeros((len(q), 2), np.float32), np.zeros(len(q), np.int32), np.zeros(len(q), np.float32)
         self.ctx._chk(self.ctx.L.vb_kdtree_nearest(self.h, _ptr(q), len(q), max_d2, _ptr(pt), _ptr(idx), _ptr(d2)))
         return pt, idx, d2
+
+    def knn(self, q, k, max_d2=np.inf):
+        """-> (idx [nq][k] original indices or -1, d2 [nq][k], count [nq])."""
+        q = _f32(q).reshape(-1, 2)
+        idx, d2, cnt = np.zeros((len(q), k), np.int32), np.zeros((len(q), k), np.float32), np.zeros(len(q), np.uint32)
+        self.ctx._chk(self.ctx.L.vb_kdtree_knn(self.h, _ptr(q), len(q), k, max_d2, _ptr(idx), _ptr(d2), _ptr(cnt)))
+        return idx, d2, cnt
 
     def radius(self, q, r, cap=None):
         q = _f32(q).reshape(-1, 2)
