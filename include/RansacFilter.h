@@ -55,5 +55,9 @@ class RansacFilter {
 // returns to one fresh std::random_device value per call.
 void vslam_b200_set_ransac_seed(unsigned long long seed);
 void vslam_b200_clear_ransac_seed();
+// Opt-in, NOT reference behaviour: VB_RANSAC_HARTLEY (1) normalises every 8-point sample (the `//TODO: normalize` at reference
+// src/RansacFilter.cpp:40), VB_RANSAC_SAMPSON (2) replaces the mis-parenthesised residual of :125-126 by the true Sampson
+// distance (threshold then in squared pixels). 0 (default) is the reference's behaviour.
+void vslam_b200_set_ransac_flags(unsigned flags);
 
 #endif

@@ -1,5 +1,5 @@
 """Bounded counting in the pair pipeline (k_bq_init / k_count_queue): hypotheses that provably cannot reach the largest
-inlier count are abandoned early. The result of find_fundamental (src/ransac.cpp:36-66: winner, inlier count, score, F, mask
+inlier count are abandoned early. The result of find_fundamental (src/RansacFilter.cpp:36-67: winner, inlier count, score, F, mask
 and the compacted matches) must not change by one bit — against the same call with the bound switched off, and against the
 CPU oracle. Option ransac_prune = 2 forces the bounded path for every batch size (by default it runs for batches that fill the
 machine), prune_rounds / prune_growth16 move the checkpoints, prune_item_chunks sizes the queue's work items (vb_set_option)."""

@@ -264,13 +264,15 @@ TC_SHAPES = [(1, 2), (1, 7), (3, 8), (5, 9), (255, 239), (256, 240), (257, 241),
              (256, 8), (300, 1000), (3000, 239), (3000, 241), (1000, 16383), (2500, 16384), (513, 720), (100, 961)]
 
 
+@pytest.mark.parametrize("drain", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n1,n2", TC_SHAPES)
-def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, n1, n2):
+def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, n1, n2, drain):
     """The tcgen05 matcher (k_knn2_tc4 + k_knn2_tc_fix) forced onto shapes the size heuristic would send to the popcount
     kernel: n1 != n2, n2 around the 240-column tile and the 8-column group, n2 < one tile, n1 around the 256-query block, the
     n2 = 16 384 key limit; duplicated train rows straddling group and tile boundaries (ties to the lower index).
     BFMatcher knnMatch k = 2 order, reference src/Frame.cpp:83-85; ratio test :91."""
     ctx.set_option("hamming_tc", 1)
+    ctx.set_option("tc_drain", drain)
     rng = np.random.default_rng(n1 * 131 + n2)
     d2 = synth.random_descriptors(rng, n2)
     d1 = synth.random_descriptors(rng, n1)
@@ -688,7 +690,8 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
 
 
 @pytest.mark.parametrize("opts", [dict(count_packed=0, score_packed=0, hamming_fp4=0), dict(tc_fix8=0), dict(hamming_qpt=1, hamming_tc=0),
-                                  dict(hamming_qpt=4, hamming_tc=0)])
+                                  dict(hamming_qpt=4, hamming_tc=0), dict(tc_drain=1), dict(tc_drain=2), dict(tc_drain=3),
+                                  dict(tc_drain=4)])
 def test_alternative_kernels_agree_with_oracle(ctx, oracle, opts):
     """The code paths behind vb_set_option — k_count<2> / k_score<2> (scalar-instruction versions), the fp8 matcher, the
     two-group fix pass on the match path, the popcount matcher's queries-per-thread variants — still agree with the oracle."""

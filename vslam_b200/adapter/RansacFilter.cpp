@@ -32,6 +32,11 @@ void vslam_b200_set_ransac_seed(unsigned long long seed) {
 }
 void vslam_b200_clear_ransac_seed() { g_seed_fixed = false; }
 
+// Opt-in repairs of the reference's own TODOs (VB_RANSAC_HARTLEY | VB_RANSAC_SAMPSON, include/vslam_b200.h); 0 = the
+// reference's behaviour, which is the default.
+static unsigned g_ransac_flags = 0;
+void vslam_b200_set_ransac_flags(unsigned flags) { g_ransac_flags = flags; }
+
 RansacFilter::RansacFilter(const int min_items, const int max_iterations, const float threshold)
     : min_items(min_items), max_iterations(max_iterations), threshold(threshold) {}
 
@@ -65,9 +70,9 @@ void RansacFilter::find_fundamental(const std::vector<cv::Point2f> &p1, const st
     std::vector<uint8_t> mask(matches.size() ? matches.size() : 1);
     int32_t n_in = 0, best = -1;
     float score = 0.f;
-    const int rc = vb_ransac_fundamental(context(), a.data(), (uint32_t)p1.size(), b.data(), (uint32_t)p2.size(), mm.data(),
-                                         (uint32_t)matches.size(), min_items, (uint32_t)(max_iterations > 0 ? max_iterations : 0),
-                                         threshold, next_seed(), F, mask.data(), &n_in, &score, &best);
+    const int rc = vb_ransac_fundamental_ex(context(), a.data(), (uint32_t)p1.size(), b.data(), (uint32_t)p2.size(), mm.data(),
+                                            (uint32_t)matches.size(), min_items, (uint32_t)(max_iterations > 0 ? max_iterations : 0),
+                                            threshold, next_seed(), g_ransac_flags, F, mask.data(), &n_in, &score, &best);
     // No accepted hypothesis: the reference leaves `fundamental` empty and `inliers` as passed (:59-65).
     // Fewer matches than min_items is undefined behaviour there; here it is the same quiet no-op.
     if (rc == VB_ERR_NO_MODEL || rc == VB_ERR_TOO_FEW) return;

@@ -329,8 +329,16 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
 //      accumulator at 64 B/clk per scheduler) and ALU work (420 clk) of a step run one after the other.
 //   1  16-column slices through two rotating 16-register buffers: slice s+1 is in flight while slice s is reduced, so the
 //      TMEM port and the ALU pipe of a scheduler overlap inside a step, and half as many raw registers are live.
-template <int DRAIN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+//   4  24 draining warps (6 per scheduler, 40-column parts) instead of 16: the profile of variants 0/1 shows the drain
+//      latency-bound per warp (one instruction per ~6.4 cycles: dependency waits, branch resolution, instruction fetch)
+//      with only four warps per scheduler to hide it behind; three buffers (16 + 16 + 8 registers) so that all of a part's
+//      loads are in flight at once, and the masked path (last tile only) kept out of the hot loop.
+constexpr int T4_THREADS_WIDE = 128 + 32 * 24;
+// SVC_HI puts the four service warps (TMA producer, UMMA issuer, TMEM allocator, spare) at the HIGHEST warp ids of the CTA
+// instead of the lowest: the warp arbiter of a scheduler prefers the highest warp id among eligible warps, and the one thread
+// that issues the UMMAs shares its scheduler with four draining warps that almost always have an instruction ready.
+template <int DRAIN, bool SVC_HI = false>
+__global__ void __launch_bounds__(DRAIN == 4 ? T4_THREADS_WIDE : TC_THREADS, 1)
 k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
            uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -341,7 +349,10 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t bar_a = sBar, bar_afree = sBar + 8, bar_tfull = sBar + 16, bar_tempty = sBar + 32, s_tmem = sBar + 48,
                    bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES;
 
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t NDW = (DRAIN == 4) ? 24u : 16u;   // draining warps
+    // role index: 0..3 = service warps, 4.. = draining warps ((wid + 4) & 3 == wid & 3, so the TMEM lane quadrant is unchanged)
+    const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
     const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
     const uint32_t ntiles = (n2 + T4_NCOLS - 1) / T4_NCOLS;
 
@@ -354,7 +365,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : 4 * T4_PARTS);   // draining warps that read each accumulator
+            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
@@ -435,7 +446,67 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         const uint32_t cw = wide ? 64 : T4_NCOLS - 192;
         uint32_t raw0[32], raw1[32];
         uint32_t g = 0;
-        if (DRAIN == 3) {
+        if (DRAIN == 4) {
+            const uint32_t part6 = ew >> 2;                 // 0..5: columns [40 part6, 40 part6 + 40) of both accumulators
+            const uint32_t pc0 = part6 * 40u;
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+            uint32_t(&rc)[8] = *reinterpret_cast<uint32_t(*)[8]>(&raw0[16]);
+            const uint32_t lane_base = acc0 + ((quad * 32u) << 16) + pc0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
+                float r0[2] = {TC_KEY_NONE, TC_KEY_NONE}, r1[2] = {TC_KEY_NONE, TC_KEY_NONE};
+                float tbase = (float)pc0 + TC_KEY_BIAS;
+                for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)T4_NCOLS) {
+                    const uint32_t tile0 = j * T4_NCOLS + pc0;
+                    const bool dead = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + 40u > n2;
+                    const uint32_t nvalid = dead ? 0 : n2 - tile0;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t taddr = lane_base + h * T4_NCOLS;
+                        mbar_wait(bar_tfull + 8 * h, g & 1);
+                        tc_fence_after();
+                        if (!dead) {
+                            tmem_ld16(taddr, ra);
+                            tmem_ld16(taddr + 16, rb);
+                            tmem_ld8(taddr + 32, rc);
+                            tmem_wait_ld_regs16(ra);
+                            tmem_wait_ld_regs16(rb);
+                            tmem_wait_ld_regs8(rc);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                        if (dead) continue;
+                        if (!masked) {
+                            drain_chunk<0, false, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            drain_chunk<16, false, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                            drain_chunk<32, false, 8>(rc, nvalid, tbase, r0[h], r1[h]);
+                        } else {
+                            drain_chunk<0, true, 16>(ra, nvalid, tbase, r0[h], r1[h]);
+                            drain_chunk<16, true, 16>(rb, nvalid, tbase, r0[h], r1[h]);
+                            drain_chunk<32, true, 8>(rc, nvalid, tbase, r0[h], r1[h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t q = qb + h * 128;
+                    if (q < n1) {
+                        uint32_t out[2];
+                        const float ks[2] = {r0[h], r1[h]};
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const uint32_t ki = __float2uint_rz(ks[i]);
+                            out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                        : 0xffffffffu;
+                        }
+                        part[((size_t)p * 6 + part6) * n1 + q] = make_uint2(out[0], out[1]);
+                    }
+                }
+            }
+        } else if (DRAIN == 3) {
             // Dedicated warps: of the four draining warps on a scheduler (= TMEM lane quadrant) two serve accumulator 0
             // and two accumulator 1, each taking 120 of its accumulator's 240 columns in 16-column slices (the register
             // scoreboard lets slice s+1 load while slice s is reduced). The two accumulators fill half a step apart, so the
@@ -752,6 +823,10 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
+        VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
+        VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         ctx->func_attr_done |= 1u;
     }
     const uint32_t P = pl.P, n1 = pl.n1, n2 = pl.n2;
@@ -760,8 +835,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    const int drain = (int)ctx->opt("tc_drain", 1);
-    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
+    const int drain = (int)ctx->opt("tc_drain", 0);   // the five organisations time within 3 % of each other, 3 excepted
+    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
@@ -803,7 +878,16 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     const int dbg = 0;
 #endif
     ctx->prof_begin("hamming");
-    if (fp4 && drain == 3)
+    const bool svc_hi = ctx->opt("tc_svc_hi", 0) != 0;
+    if (fp4 && svc_hi && drain == 4)
+        k_knn2_tc4<4, true><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && svc_hi && drain == 1)
+        k_knn2_tc4<1, true><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && svc_hi && drain == 0)
+        k_knn2_tc4<0, true><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 4)
+        k_knn2_tc4<4><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 3)
         k_knn2_tc4<3><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 2)
         k_knn2_tc4<2><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);

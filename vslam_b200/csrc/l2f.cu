@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(L2_THREADS) k_l2_partial(const float *__restri
     }
 }
 
-__global__ void __launch_bounds__(256) k_l2_finish(const ulonglong2 *__restrict__ part, uint32_t nsplits, uint32_t n1,
+__global__ void __launch_bounds__(1024) k_l2_finish(const ulonglong2 *__restrict__ part, uint32_t nsplits, uint32_t n1,
                                                    double ratio, int32_t *__restrict__ knn_idx, float *__restrict__ knn_dist,
                                                    int2 *__restrict__ tent, uint32_t *__restrict__ m_out,
                                                    const float2 *__restrict__ p1, const float2 *__restrict__ p2,
                                                    float4 *__restrict__ corr) {
-    __shared__ int s_scan[8];
+    __shared__ int s_scan[32];
     __shared__ int s_base;
     const uint32_t tid = threadIdx.x;
     const int lane = tid & 31, w = tid >> 5;
@@ -176,7 +176,8 @@ static int l2_device(vb_ctx *ctx, const float *d1_d, uint32_t n1, const float *d
     int32_t *kidx = ctx->ws[WS_KNN].as<int32_t>();
     float *kdist = reinterpret_cast<float *>(kidx + (size_t)n1 * 2);
     ctx->prof_begin("finish");
-    k_l2_finish<<<1, 256, 0, ctx->stream>>>(ctx->ws[WS_L2C].as<ulonglong2>(), nsplits, n1, ratio, kidx, kdist,
+    // one CTA (the compaction is ordered); 1 024 threads for config-3 sized inputs: 20 rounds instead of 79
+    k_l2_finish<<<1, n1 > 2048 ? 1024 : 256, 0, ctx->stream>>>(ctx->ws[WS_L2C].as<ulonglong2>(), nsplits, n1, ratio, kidx, kdist,
                                             ctx->ws[WS_TENT].as<int2>(), ctx->ws[WS_M].as<uint32_t>(), p1_d, p2_d,
                                             p1_d ? ctx->ws[WS_CORR].as<float4>() : nullptr);
     ctx->prof_end("finish");
