@@ -78,3 +78,31 @@ def test_two_rank_gloo_equals_single(tmp_path, oracle):
         o = oracle.match_features(pts[i], desc[i], pts[i + 1], desc[i + 1], 0.7, 8, 32, 10.0, 77 + i)
         assert got["n_matches"][i] == max(o["n"], 0) and got["best_hyp"][i] == o["best"]
         assert np.array_equal(got["F"][i].view(np.uint32), o["F"].reshape(-1).view(np.uint32))
+
+
+def test_reflected_sequence_is_made_of_genuine_pairs():
+    """bench.py's config-4 sequence (10 001 frames out of a 1 025-frame base walked forwards and backwards): every
+    consecutive pair of the long sequence is a consecutive pair of the base, whatever range a rank takes."""
+    import bench
+    period = 1024
+    full = bench.reflected_frames(0, 10001, period)
+    assert full.min() == 0 and full.max() == period
+    assert (np.abs(np.diff(full)) == 1).all()
+    for world in (1, 2, 3, 8):
+        from vslam_b200.sequence import shard_pairs
+        got = []
+        for r in range(world):
+            b, e = shard_pairs(10000, world)[r]
+            idx = bench.reflected_frames(b, e - b + 1, period)          # the rank's frames incl. the one-frame halo
+            assert np.array_equal(idx, full[b:e + 1])
+            got.append(e - b)
+        assert sum(got) == 10000
+
+
+def test_multi_partition_matches_header_contract():
+    """vb_multi cuts P pairs into ranges [P*w/n, P*(w+1)/n) (multi.cu); ranges tile [0, P) without gaps for any n, and a
+    range's packed matches start at first * k (include/vslam_b200.h)."""
+    for P in (0, 1, 5, 1024, 10000):
+        for n in (1, 2, 3, 8):
+            firsts = [P * w // n for w in range(n + 1)]
+            assert firsts[0] == 0 and firsts[-1] == P and all(a <= b for a, b in zip(firsts, firsts[1:]))
