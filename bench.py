@@ -7,7 +7,9 @@ Workload (BASELINE.json configs[1]): every consecutive pair of a synthetic monoc
 (--frames frames, frames-1 pairs) in a fixed number of batched kernel launches. Per-rank inputs are
 ~205 MB (larger than the 126 MB L2), so consecutive steps do not find their inputs in L2.
 
-  value  pairs/s, inputs resident in HBM (vb_pairs_run_d), CUDA events on the launching stream
+  value  pairs/s, inputs resident in HBM, steps issued as a streaming caller does (vb_pairs_submit_d / vb_pairs_wait, two
+         in flight: the counting of one step runs beside the matcher of the next), CUDA events on the launching stream;
+         value_one_stream = the same steps one after the other through vb_pairs_run_d (round 1's measurement)
   e2e    pairs/s through the host-pointer C-ABI (vb_pairs_submit / vb_pairs_wait, two submissions in flight): pinned
          host buffers, H2D of every frame and D2H of results + compact matches inside the timed region, every step;
          e2e.frac_of_copy_ceiling compares it with plain cudaMemcpyAsync traffic of the same byte counts on this box.
@@ -274,6 +276,26 @@ def main():
         ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, pts_d.data_ptr(), desc_d.data_ptr(), nframes, k, nbytes, C.byref(prm),
                                       res_d.data_ptr(), out_d.data_ptr()))
 
+    # device-resident steps as a streaming caller issues them: two submissions in flight (vb_pairs_submit_d), so that the
+    # counting and the small kernels of one step run beside the matcher of the next; second set of output buffers
+    res_d2 = torch.zeros_like(res_d)
+    out_d2 = torch.zeros_like(out_d)
+    dev_outs = [(res_d, out_d), (res_d2, out_d2)]
+
+    def steps_device_stream(n):
+        def sub(i):
+            t = C.c_int(-1)
+            r_, o_ = dev_outs[i & 1]
+            ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, pts_d.data_ptr(), desc_d.data_ptr(), nframes, k, nbytes, C.byref(prm),
+                                             r_.data_ptr(), o_.data_ptr(), C.byref(t)))
+            return t.value
+        tk = sub(0)
+        for i in range(1, n):
+            tn = sub(i)
+            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, None))
+            tk = tn
+        ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, None))
+
     def step_e2e():
         ctx._chk(ctx.L.vb_pairs_run(ctx.h, pts_h.data_ptr(), desc_h.data_ptr(), nframes, k, nbytes, C.byref(prm),
                                     res_h.data_ptr(), out_h.data_ptr()))
@@ -291,17 +313,28 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ------------------------------------------------------------
+    # (a) one step after the other on one stream (vb_pairs_run_d) — round 1's measurement, kept as value_one_stream
     for _ in range(args.warmup):
         step_device()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.ransac_prune_stats(reset=True)
-    launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    e1.record(stream)
+    barrier()
+    ms_one_stream = max_over_ranks(e0.elapsed_time(e1))
+    # (b) the same steps with two submissions in flight (vb_pairs_submit_d / vb_pairs_wait): `value`. vb_pairs_wait returns
+    # when the ticket's kernels have finished, so the closing event is recorded after all of the timed work.
+    steps_device_stream(max(args.warmup, 4))
+    barrier()
+    ctx.ransac_prune_stats(reset=True)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    steps_device_stream(args.steps)
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -505,6 +538,10 @@ def main():
                 "bounded_counting": {"evaluations_done": evals_done, "evaluations_full": evals_full,
                                      "fraction": (evals_done / evals_full) if evals_full else None},
                 "single_pair_match_features_ms": single_ms,
+                "value_one_stream": {"value": world * P * args.steps / (ms_one_stream * 1e-3), "unit": UNIT,
+                                     "ms_per_step": ms_one_stream / args.steps,
+                                     "api": "vb_pairs_run_d back to back on one stream (round 1's `value`); `value` itself = "
+                                            "vb_pairs_submit_d / vb_pairs_wait, two submissions in flight on two compute streams"},
                 "check": {"pairs_ok": ok_pairs, "pairs": P, "mean_final_matches": mean_matches,
                           "mean_tentative": sum_tent / P}}
         line.update(e2e_other)
@@ -580,9 +617,22 @@ def config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, b
     out_d = torch.zeros((max(np_r, 1), k, 2), dtype=torch.int32, device=dev)
     prm4 = ctx.params(0.7, 8, args.hyps, args.threshold, 1 + b)
 
-    def dev_pass():
-        ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, sp_d.data_ptr(), sd_d.data_ptr(), np_r + 1, k, nbytes, C.byref(prm4),
-                                      res_d.data_ptr(), out_d.data_ptr()))
+    CH = 1024
+    chunks = [(c, min(c + CH, np_r)) for c in range(0, np_r, CH)]
+    RS = PAIR_RESULT_DTYPE.itemsize
+
+    def dev_pass():   # 1 024-pair submissions, two in flight (vb_pairs_submit_d), results written in place
+        tickets = []
+        for c0, c1 in chunks:
+            t = C.c_int(-1)
+            pc = ctx.params(0.7, 8, args.hyps, args.threshold, 1 + b + c0)
+            ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, sp_d.data_ptr() + c0 * k * 8, sd_d.data_ptr() + c0 * k * nbytes, c1 - c0 + 1, k,
+                                             nbytes, C.byref(pc), res_d.data_ptr() + c0 * RS, out_d.data_ptr() + c0 * k * 8, C.byref(t)))
+            tickets.append(t.value)
+            if len(tickets) == 2:
+                ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tickets.pop(0), None))
+        for t in tickets:
+            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, t, None))
     dev_pass()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -594,9 +644,7 @@ def config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, b
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1)) / reps
     r4 = res_d.cpu().numpy().view(PAIR_RESULT_DTYPE)[:np_r]
-    # end to end: 1 024-pair chunks (one-frame halo each), two in flight
-    CH = 1024
-    chunks = [(c, min(c + CH, np_r)) for c in range(0, np_r, CH)]
+    # end to end: the same chunks from pinned host memory
     res_h = torch.zeros(max(np_r, 1) * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     off_h = torch.zeros(max(np_r, 1), dtype=torch.int32).pin_memory()
     m16_h = torch.zeros((max(np_r, 1) * k, 2), dtype=torch.int16).pin_memory()

@@ -63,6 +63,8 @@ int vb_synchronize(vb_ctx *ctx);
  *   prune_first_chunks, prune_first16, prune_growth16, prune_rounds, prune_item_chunks   its checkpoint schedule
  *   count_packed 0, score_packed 0   scalar-instruction versions of the counting / scoring kernels
  *   kd_lanes_per_query 1/8/32        k-d tree 1-NN: lanes that share one query (A/B of the thread-per-query mapping)
+ *   tc_drain 0..4, tc_svc_hi 0/1     organisation of the tensor matcher's drain / placement of its service warps
+ *   pairs_overlap 0                  vb_pairs_submit[_d]: every submission on one compute stream instead of alternating two
  * A build with -DVB_TUNING adds timing-only options (tc_dbg, prune_ctas_per_sm, pairs_twin, pairs_split). Unknown names
  * return VB_ERR_INVALID. vb_reset_options restores every built-in rule. */
 int vb_set_option(vb_ctx *ctx, const char *name, long long value);
@@ -262,6 +264,13 @@ int vb_pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t
                     const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,
                     uint64_t cap_matches, int *ticket);
 int vb_pairs_wait(vb_ctx *ctx, int ticket, uint64_t *total_matches);
+/* The same with device-resident inputs and outputs (arguments as vb_pairs_run_d; nothing is copied). An odd ticket's work
+ * runs on an internal stream that first waits for everything queued on the context's stream at submission time;
+ * vb_pairs_wait(ticket) returns once its kernels have finished (*total_matches is not written). Two consecutive submissions
+ * overlap on the GPU — the counting and the small kernels of one beside the matcher of the other — which a sequence of
+ * vb_pairs_run_d calls on one stream cannot. */
+int vb_pairs_submit_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint32_t nframes, uint32_t k, uint32_t bytes,
+                      const vb_pair_params *params, vb_pair_result *results_d, int32_t *out_matches_d, int *ticket);
 /* submit + wait */
 int vb_pairs_run_compact(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
                          const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,

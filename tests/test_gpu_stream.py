@@ -124,3 +124,46 @@ def test_multi_equals_single_context(ctx, devices):
         assert np.array_equal(m162[int(off2[0]):int(off2[0]) + int(res2["n_matches"][0])].astype(np.int32), out_b[0][:res_b["n_matches"][0]])
     finally:
         m.close()
+
+
+def test_device_resident_submissions_overlap_and_agree(ctx):
+    """vb_pairs_submit_d: two device-resident submissions in flight on two compute streams (the context's and its twin's) ==
+    vb_pairs_run_d on one stream, bit for bit; option pairs_overlap = 0 puts both on one stream with the same results."""
+    import torch
+    from vslam_b200.lib import PAIR_RESULT_DTYPE, VbError
+    nframes, k = 40, 1500
+    seqs = [synth.sequence(nframes, k, s) for s in (11, 12, 13)]
+    prm = ctx.params(0.7, 8, 128, 10.0, 21)
+    P = nframes - 1
+    dev = [(torch.from_numpy(p).cuda(), torch.from_numpy(d).cuda()) for p, d in seqs]
+
+    def outs():
+        return torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda"), torch.zeros((P, k, 2), dtype=torch.int32, device="cuda")
+
+    want = []
+    for pd, dd in dev:
+        r, o = outs()
+        ctx._chk(ctx.L.vb_pairs_run_d(ctx.h, C.c_void_p(pd.data_ptr()), C.c_void_p(dd.data_ptr()), nframes, k, 32, C.byref(prm),
+                                      C.c_void_p(r.data_ptr()), C.c_void_p(o.data_ptr())))
+        ctx.synchronize()
+        want.append((r.cpu().numpy().view(PAIR_RESULT_DTYPE), o.cpu().numpy()))
+    for overlap in (1, 0):
+        ctx.set_option("pairs_overlap", overlap)
+        got = [outs() for _ in dev]
+        tickets = []
+        for (pd, dd), (r, o) in zip(dev, got):
+            t = C.c_int(-1)
+            if len(tickets) == 2:
+                ctx.pairs_wait(tickets.pop(0))
+            ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, C.c_void_p(pd.data_ptr()), C.c_void_p(dd.data_ptr()), nframes, k, 32, C.byref(prm),
+                                             C.c_void_p(r.data_ptr()), C.c_void_p(o.data_ptr()), C.byref(t)))
+            tickets.append(t.value)
+        with pytest.raises(VbError):
+            t = C.c_int(-1)
+            ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, C.c_void_p(dev[0][0].data_ptr()), C.c_void_p(dev[0][1].data_ptr()), nframes, k, 32,
+                                             C.byref(prm), C.c_void_p(got[0][0].data_ptr()), None, C.byref(t)))
+        for t in tickets:
+            ctx.pairs_wait(t)
+        for (r, o), (wr, wo) in zip(got, want):
+            rr = r.cpu().numpy().view(PAIR_RESULT_DTYPE)
+            _same(rr, [o.cpu().numpy()[i, :n] for i, n in enumerate(rr["n_matches"])], wr, wo)

@@ -80,7 +80,7 @@ int vb_destroy(vb_ctx *c) {
 // force each of them); the second group exists only in a -DVB_TUNING build (measurement aids: timing floors, schedules).
 static const char *const kOptions[] = {
     "hamming_tc", "hamming_fp4", "tc_fix8", "hamming_qpt", "l2_tc", "ransac_lazy", "ransac_prune", "prune_first_chunks",
-    "prune_first16", "prune_growth16", "prune_rounds", "prune_item_chunks", "count_packed", "score_packed", "kd_lanes_per_query", "tc_drain", "tc_svc_hi",
+    "prune_first16", "prune_growth16", "prune_rounds", "prune_item_chunks", "count_packed", "score_packed", "kd_lanes_per_query", "tc_drain", "tc_svc_hi", "pairs_overlap",
 #ifdef VB_TUNING
     "tc_dbg", "prune_ctas_per_sm", "pairs_twin", "pairs_split",
 #endif
@@ -115,7 +115,7 @@ int vb_synchronize(vb_ctx *c) {
     return VB_OK;
 }
 
-uint64_t vb_launch_count(const vb_ctx *c) { return c ? c->launches : 0; }
+uint64_t vb_launch_count(const vb_ctx *c) { return c ? c->launches + (c->twin ? c->twin->launches : 0) : 0; }
 
 int vb_profile_enable(vb_ctx *c, int on) {
     VB_REQUIRE(c != nullptr, VB_ERR_INVALID, "ctx is NULL");

@@ -835,7 +835,9 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    const int drain = (int)ctx->opt("tc_drain", 0);   // the five organisations time within 3 % of each other, 3 excepted
+    // the organisations time within 3 % of each other (3 excepted); 1 needs 68 registers instead of 93,
+    // which leaves room for another submission's kernels beside the matcher (stream.cu)
+    const int drain = (int)ctx->opt("tc_drain", 1);
     const uint32_t nparts = fp4 ? (drain == 3 ? 2u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();

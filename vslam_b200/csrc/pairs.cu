@@ -118,8 +118,6 @@ int vb_pairs_run_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     if (twin) {
         VB_CUDA(cudaEventRecord(ctx->events[1], ctx->twin->stream));
         VB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[1], 0));
-        ctx->launches += ctx->twin->launches;
-        ctx->twin->launches = 0;
     }
     return VB_OK;
 }
@@ -248,8 +246,6 @@ int vb_pairs_run(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     VB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->twin) {
         VB_CUDA(cudaStreamSynchronize(ctx->twin->stream));
-        ctx->launches += ctx->twin->launches;
-        ctx->twin->launches = 0;
     }
     return VB_OK;
 }

@@ -45,7 +45,7 @@ EXPORTS = [
     "vb_kdtree_nearest", "vb_kdtree_nearest_d", "vb_kdtree_knn", "vb_kdtree_knn_d", "vb_kdtree_radius", "vb_kdtree_radius_d",
     "vb_knn2_hamming", "vb_match_hamming", "vb_knn2_l2f", "vb_match_l2f",
     "vb_ransac_fundamental", "vb_ransac_fundamental_ex", "vb_ransac_hypotheses", "vb_ransac_score", "vb_ransac_score_d", "vb_ransac_counts", "vb_ransac_counts_d", "vb_ransac_prune_stats", "vb_ransac_solve8", "vb_ransac_sample_sets", "vb_ransac_residual",
-    "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_wait", "vb_pairs_run_compact",
+    "vb_match_features", "vb_match_features_l2f", "vb_match_features_l2f_d", "vb_pairs_run", "vb_pairs_run_d", "vb_pairs_submit", "vb_pairs_submit_d", "vb_pairs_wait", "vb_pairs_run_compact",
     "vb_host_alloc", "vb_host_free", "vb_host_register", "vb_host_unregister",
     "vb_multi_create", "vb_multi_destroy", "vb_multi_device_count", "vb_multi_pairs_submit", "vb_multi_pairs_wait", "vb_multi_pairs_run", "vb_search_by_projection", "vb_extract_rt", "vb_triangulate", "vb_triangulate_gated", "vb_profile_enable", "vb_profile_last_ms", "vb_probe_tensor_peak",
 ]
@@ -117,6 +117,7 @@ def load_library() -> C.CDLL:
     L.vb_pairs_run.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_run_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp]
     L.vb_pairs_submit.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(C.c_int)]
+    L.vb_pairs_submit_d.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, C.POINTER(C.c_int)]
     L.vb_pairs_wait.argtypes = [vp, C.c_int, C.POINTER(u64)]
     L.vb_pairs_run_compact.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(PairParams), vp, vp, vp, u64, C.POINTER(u64)]
     L.vb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
