@@ -10,7 +10,7 @@ Workload (BASELINE.json configs[1]): every consecutive pair of a synthetic monoc
   value  pairs/s, inputs resident in HBM, steps issued as a streaming caller does (vb_pairs_submit_d / vb_pairs_wait, two
          in flight: the counting of one step runs beside the matcher of the next), CUDA events on the launching stream;
          value_one_stream = the same steps one after the other through vb_pairs_run_d (round 1's measurement)
-  e2e    pairs/s through the host-pointer C-ABI (vb_pairs_submit / vb_pairs_wait, two submissions in flight): pinned
+  e2e    pairs/s through the host-pointer C-ABI (vb_pairs_submit / vb_pairs_wait, three submissions in flight): pinned
          host buffers, H2D of every frame and D2H of results + compact matches inside the timed region, every step;
          e2e.frac_of_copy_ceiling compares it with plain cudaMemcpyAsync traffic of the same byte counts on this box.
          (e2e_blocking_call = the blocking vb_pairs_run, e2e_pageable = the same calls on pageable memory.)
@@ -45,6 +45,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 METRIC = "frame pairs/sec (match+RANSAC) at 5k kpts"
 UNIT = "pairs/s"
+E2E_DEPTH = 3   # host-pointer submissions in flight: one uploading, two computing (the library allows three per context)
 DTYPE = "u8 descriptors as e2m1 +-1 on tcgen05 kind::mxf4 (exact integer Hamming) + f32/f64 residual"
 
 
@@ -396,29 +397,30 @@ def main():
     shares = {n: (v * (P / P_prof) / step_ms if v and v > 0 else None) for n, v in kt.items()}
 
     # ---- end to end through the host-pointer C ABI ---------------------------------------------------------------
-    # Streaming submission: two tickets in flight, so the upload of step i+1 and the download of step i-1 overlap the kernels
-    # of step i. Every step uploads all of its frames from pinned host memory and downloads every pair's result + matches.
+    # Streaming submission: three tickets in flight — one uploading while two compute on the context's two streams — so the
+    # upload of step i+2 and the download of step i-1 overlap the kernels of steps i and i+1. Every step uploads all of its frames from pinned host memory and downloads every pair's result + matches.
     e_steps = max(20, args.steps)
     outs = [(torch.zeros(P * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
              torch.zeros(P, dtype=torch.int32).pin_memory(),
-             torch.zeros((P * k, 2), dtype=torch.int16).pin_memory()) for _ in range(2)]
+             torch.zeros((P * k, 2), dtype=torch.int16).pin_memory()) for _ in range(E2E_DEPTH)]
 
     def submit(i, pp, dd, oo):
         t = C.c_int(-1)
-        r_, o_, m_ = oo[i & 1]
+        r_, o_, m_ = oo[i % len(oo)]
         ctx._chk(ctx.L.vb_pairs_submit(ctx.h, pp, dd, nframes, k, nbytes, C.byref(prm), r_.data_ptr(), o_.data_ptr(),
                                        m_.data_ptr(), P * k, C.byref(t)))
         return t.value
 
     def stream_steps(n, pp, dd, oo):
         """n pipelined steps; returns the match count of the last one."""
-        tk = submit(0, pp, dd, oo)
         tot = C.c_uint64(0)
-        for i in range(1, n):
-            tn = submit(i, pp, dd, oo)
-            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, C.byref(tot)))
-            tk = tn
-        ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tk, C.byref(tot)))
+        inflight = []
+        for i in range(n):
+            inflight.append(submit(i, pp, dd, oo))
+            if len(inflight) == len(oo):
+                ctx._chk(ctx.L.vb_pairs_wait(ctx.h, inflight.pop(0), C.byref(tot)))
+        while inflight:
+            ctx._chk(ctx.L.vb_pairs_wait(ctx.h, inflight.pop(0), C.byref(tot)))
         return int(tot.value)
 
     stream_steps(max(3, args.warmup), pts_h.data_ptr(), desc_h.data_ptr(), outs)
@@ -428,7 +430,7 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()   # sampled every 20 ms across both timed regions (device-resident and end-to-end)
-    last = outs[(e_steps - 1) & 1]
+    last = outs[(e_steps - 1) % len(outs)]
     res_e = last[0].numpy().view(PAIR_RESULT_DTYPE)
     off_e = last[1].numpy().view(np.uint32)
     m16_e = last[2].numpy().view(np.uint16)
@@ -437,7 +439,7 @@ def main():
     d2h_bytes = int(P * PAIR_RESULT_DTYPE.itemsize + P * 4 + total_matches * 4)
     e2e = {"value": world * P * e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": d2h_bytes, "steps": e_steps,
-           "api": "vb_pairs_submit / vb_pairs_wait, 2 submissions in flight, pinned host buffers, compact uint16 matches",
+           "api": "vb_pairs_submit / vb_pairs_wait, %d submissions in flight, pinned host buffers, compact uint16 matches" % E2E_DEPTH,
            "frac_of_device_resident": (world * P * e_steps / e2e_s) / value}
     # the ceiling of this box for the same traffic: plain cudaMemcpyAsync H2D + D2H of the same byte counts, both
     # directions at once, every rank at the same time, nothing computing
@@ -658,7 +660,7 @@ def config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, b
                                            C.byref(pc), res_h.data_ptr() + c0 * PAIR_RESULT_DTYPE.itemsize,
                                            off_h.data_ptr() + c0 * 4, m16_h.data_ptr() + c0 * k * 4, (c1 - c0) * k, C.byref(t)))
             tickets.append(t.value)
-            if len(tickets) == 2:
+            if len(tickets) == E2E_DEPTH:
                 ctx._chk(ctx.L.vb_pairs_wait(ctx.h, tickets.pop(0), C.byref(tot)))
         for t in tickets:
             ctx._chk(ctx.L.vb_pairs_wait(ctx.h, t, C.byref(tot)))
@@ -688,7 +690,7 @@ def config4_strong(args, ctx, torch, dev, stream, pts, desc, prm, rank, world, b
 
 def multi_stage(args, torch, pts, desc, prm, world, P, k, nbytes):
     """The weak-scaling workload (world x P pairs) driven by ONE process through vb_multi: one host thread + context + streams
-    per GPU, every GPU's results landing in one host array (the host gather). Two submissions in flight."""
+    per GPU, every GPU's results landing in one host array (the host gather). Three submissions in flight."""
     from vslam_b200.lib import PAIR_RESULT_DTYPE, Multi
     tp = world * P
     fidx = reflected_frames(0, tp + 1, pts.shape[0] - 1)
@@ -696,30 +698,31 @@ def multi_stage(args, torch, pts, desc, prm, world, P, k, nbytes):
     dh = torch.from_numpy(np.ascontiguousarray(desc[fidx])).pin_memory()
     outs = [(torch.zeros(tp * PAIR_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
              torch.zeros(tp, dtype=torch.int32).pin_memory(),
-             torch.zeros((tp * k, 2), dtype=torch.int16).pin_memory()) for _ in range(2)]
+             torch.zeros((tp * k, 2), dtype=torch.int16).pin_memory()) for _ in range(E2E_DEPTH)]
     m = Multi(list(range(world)))
     try:
         def submit(i):
             t = C.c_int(-1)
-            r_, o_, m_ = outs[i & 1]
+            r_, o_, m_ = outs[i % len(outs)]
             m._chk(m.L.vb_multi_pairs_submit(m.h, ph.data_ptr(), dh.data_ptr(), tp + 1, k, nbytes, C.byref(prm), r_.data_ptr(),
                                              o_.data_ptr(), m_.data_ptr(), tp * k, C.byref(t)))
             return t.value
 
         def steps(n):
-            tk, tot = submit(0), C.c_uint64(0)
-            for i in range(1, n):
-                tn = submit(i)
-                m._chk(m.L.vb_multi_pairs_wait(m.h, tk, C.byref(tot)))
-                tk = tn
-            m._chk(m.L.vb_multi_pairs_wait(m.h, tk, C.byref(tot)))
+            tot, inflight = C.c_uint64(0), []
+            for i in range(n):
+                inflight.append(submit(i))
+                if len(inflight) == len(outs):
+                    m._chk(m.L.vb_multi_pairs_wait(m.h, inflight.pop(0), C.byref(tot)))
+            while inflight:
+                m._chk(m.L.vb_multi_pairs_wait(m.h, inflight.pop(0), C.byref(tot)))
             return int(tot.value)
         steps(3)
         n = max(10, min(args.steps, 20))
         t0 = time.perf_counter()
         tot = steps(n)
         dt = time.perf_counter() - t0
-        r = outs[(n - 1) & 1][0].numpy().view(PAIR_RESULT_DTYPE)
+        r = outs[(n - 1) % len(outs)][0].numpy().view(PAIR_RESULT_DTYPE)
         return {"value": tp * n / dt, "unit": UNIT, "steps": n, "pairs_per_step": tp, "n_gpus": world,
                 "api": "vb_multi_pairs_submit / vb_multi_pairs_wait: 1 process, %d host threads, results gathered in one host array" % world,
                 "h2d_bytes_per_step": int(ph.numel() * 4 + dh.numel()), "d2h_bytes_per_step": int(tp * 64 + tot * 4),

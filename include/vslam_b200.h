@@ -249,8 +249,10 @@ int vb_match_features_l2f_d(vb_ctx *ctx, const float *p1_xy_d, const float *d1_d
 /* ------------------------------------------------------------------------------------------------
  * Streaming submission with a compact result download — for callers that process one sequence after another (the
  * reference's main loop calls match_features once per frame, src/vslam.cpp:92; a batch of frames is one submission).
- * Up to two submissions per context are in flight: the upload of the next one and the download of the previous one
- * overlap the kernels of the current one. All pointers are HOST pointers and must stay valid until the ticket has been
+ * Up to three submissions per context are in flight (a fourth returns VB_ERR_CAPACITY until the oldest ticket has been
+ * waited for): one uploading while two compute — consecutive submissions run on two internal compute streams, the counting
+ * and the small kernels of one beside the matcher of the other (option pairs_overlap = 0: one stream) — and the download
+ * of the oldest one overlaps both. All pointers are HOST pointers and must stay valid until the ticket has been
  * waited for; copies overlap with compute only when they are pinned (vb_host_alloc / vb_host_register).
  *   results        [nframes-1]
  *   match_offsets  [nframes-1]  index (in matches, not bytes) of pair i's first match inside matches16

@@ -1,4 +1,4 @@
-"""vb_pairs_submit / vb_pairs_wait (double-buffered, compact download) and vb_multi (one host thread + context per GPU in one
+"""vb_pairs_submit / vb_pairs_wait (three submissions in flight, compact download) and vb_multi (one host thread + context per GPU in one
 process): same results, bit for bit, as the blocking vb_pairs_run and as the oracle's match_features
 (reference src/Frame.cpp:82-105), whatever the number of tickets in flight or the device list."""
 import ctypes as C
@@ -49,9 +49,9 @@ def test_compact_equals_blocking_and_oracle(ctx, oracle):
             assert np.array_equal(mc[i], o["matches"]) and np.array_equal(_bits(res_c["F"][i]), _bits(o["F"].reshape(-1)))
 
 
-def test_two_tickets_in_flight(ctx):
+def test_three_tickets_in_flight(ctx):
     from vslam_b200.lib import PAIR_RESULT_DTYPE, VbError, pinned_empty, unpack_compact
-    seqs = [synth.sequence(5, 900, s) for s in (1, 2, 3)]
+    seqs = [synth.sequence(5, 900, s) for s in (1, 2, 3, 4, 5)]
     prm = ctx.params(0.7, 8, 64, 10.0, 7)
     want = [ctx.pairs_run(p, d, prm) for p, d in seqs]
     bufs, keep = [], []
@@ -63,17 +63,19 @@ def test_two_tickets_in_flight(ctx):
         off, h4 = pinned_empty(ctx.L, (4,), np.uint32)
         m16, h5 = pinned_empty(ctx.L, (4 * 900, 2), np.uint16)
         bufs.append((pp, dd, res, off, m16)); keep += [h1, h2, h3, h4, h5]
-    t0 = ctx.pairs_submit(bufs[0][0], bufs[0][1], prm, *bufs[0][2:])
-    t1 = ctx.pairs_submit(bufs[1][0], bufs[1][1], prm, *bufs[1][2:])
-    with pytest.raises(VbError) as e:                                       # a third one needs a free slot
-        ctx.pairs_submit(bufs[2][0], bufs[2][1], prm, *bufs[2][2:])
+    sub = lambda i: ctx.pairs_submit(bufs[i][0], bufs[i][1], prm, *bufs[i][2:])
+    t0, t1, t2 = sub(0), sub(1), sub(2)                                     # one uploading, two computing (context + twin)
+    with pytest.raises(VbError) as e:                                       # a fourth one needs a free slot
+        sub(3)
     assert e.value.code == 4
-    tot0 = ctx.pairs_wait(t0)
-    t2 = ctx.pairs_submit(bufs[2][0], bufs[2][1], prm, *bufs[2][2:])
-    tot1, tot2 = ctx.pairs_wait(t1), ctx.pairs_wait(t2)
+    tots = [ctx.pairs_wait(t0)]
+    t3 = sub(3)
+    tots.append(ctx.pairs_wait(t1))
+    t4 = sub(4)
+    tots += [ctx.pairs_wait(t) for t in (t2, t3, t4)]
     with pytest.raises(VbError):
         ctx.pairs_wait(t1)                                                  # already completed
-    for (pp, dd, res, off, m16), (rb, ob), tot in zip(bufs, want, (tot0, tot1, tot2)):
+    for (pp, dd, res, off, m16), (rb, ob), tot in zip(bufs, want, tots):
         _same(res, unpack_compact(res, off, m16), rb, ob)
         assert tot == int(res["n_matches"].sum())
     for h in keep:
@@ -127,7 +129,7 @@ def test_multi_equals_single_context(ctx, devices):
 
 
 def test_device_resident_submissions_overlap_and_agree(ctx):
-    """vb_pairs_submit_d: two device-resident submissions in flight on two compute streams (the context's and its twin's) ==
+    """vb_pairs_submit_d: three device-resident submissions in flight on two compute streams (the context's and its twin's) ==
     vb_pairs_run_d on one stream, bit for bit; option pairs_overlap = 0 puts both on one stream with the same results."""
     import torch
     from vslam_b200.lib import PAIR_RESULT_DTYPE, VbError
@@ -153,12 +155,10 @@ def test_device_resident_submissions_overlap_and_agree(ctx):
         tickets = []
         for (pd, dd), (r, o) in zip(dev, got):
             t = C.c_int(-1)
-            if len(tickets) == 2:
-                ctx.pairs_wait(tickets.pop(0))
             ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, C.c_void_p(pd.data_ptr()), C.c_void_p(dd.data_ptr()), nframes, k, 32, C.byref(prm),
                                              C.c_void_p(r.data_ptr()), C.c_void_p(o.data_ptr()), C.byref(t)))
             tickets.append(t.value)
-        with pytest.raises(VbError):
+        with pytest.raises(VbError):                                            # three are in flight: no free slot
             t = C.c_int(-1)
             ctx._chk(ctx.L.vb_pairs_submit_d(ctx.h, C.c_void_p(dev[0][0].data_ptr()), C.c_void_p(dev[0][1].data_ptr()), nframes, k, 32,
                                              C.byref(prm), C.c_void_p(got[0][0].data_ptr()), None, C.byref(t)))

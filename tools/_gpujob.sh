@@ -1,6 +1,7 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2p_gpu_tests.log; cat gpurun_out/r2p_gpu_tests.log
-(time python bench.py) > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err; tail -4 gpurun_out/r2p_bench.err
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r2z_gpu_tests.log; cat gpurun_out/r2z_gpu_tests.log
+(time python bench.py) > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; tail -4 gpurun_out/r2z_bench.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r2p_bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], d['ms_per_step'], 'one_stream', d['value_one_stream'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_device_resident'])
-print('config3', d['config3']['device_resident_ms'], 'config4', d['config4']['device_resident'], d['config4']['e2e'], 'launches', d['gpu_launches'])"
+import json; d=json.loads(open('gpurun_out/r2z_bench.json').read().strip().splitlines()[-1])
+print('value', d['value'], d['ms_per_step'], 'one_stream', d['value_one_stream']['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_device_resident'], 'roof', d['roofline']['frac'])
+print('config3', d['config3']['device_resident_ms'], 'config4', d['config4']['device_resident'], d['config4']['e2e'], 'launches', d['gpu_launches'])
+print(d['kernel_ms'])"

@@ -18,7 +18,7 @@ cases = []
 for n1, n2 in shapes:
     d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8); d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
     d2[n2 // 2] = d2[3]; d1[5 % n1] = d2[3]
-    cases.append((d1, d2) + orc.knn2_hamming(d1, d2))
+    cases.append((d1, d2) + orc.knn2_hamming(d1, d2) + (orc.match_hamming(d1, d2, 0.9),))
 extra = [kv for kv in os.environ.get("TC_EXTRA", "").split(",") if kv]
 for drain in [int(x) for x in os.environ.get("TC_DRAINS", "0,1,2").split(",")]:
     ctx.reset_options()
@@ -27,9 +27,10 @@ for drain in [int(x) for x in os.environ.get("TC_DRAINS", "0,1,2").split(",")]:
     for kv in extra:
         n_, v_ = kv.split("="); ctx.set_option(n_, int(v_))
     ok = True
-    for d1, d2, oi, od in cases:
-        idx, dist = ctx.knn2_hamming(d1, d2)
+    for d1, d2, oi, od, om in cases:
+        idx, dist = ctx.knn2_hamming(d1, d2)   # (variant 6 hands callers that want the second index to variant 1)
         ok &= bool(np.array_equal(idx, oi) and np.array_equal(dist, od))
+        ok &= bool(np.array_equal(ctx.match_hamming(d1, d2, 0.9), om))
     ctx.profile(True)
     ms = []
     for it in range(4):

@@ -324,6 +324,45 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
     *reinterpret_cast<uint4 *>(dst + ((size_t)p * rows * 8 + t) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// ---- packed-integer drain (DRAIN 6) ------------------------------------------------------------------------------------
+// The ALU pipe issues one warp instruction per two cycles, and the float drain needs 13 of them per 16 columns: 447 cycles
+// per accumulator for the max trees and offers alone, against 494 cycles of UMMA time (tools/probe/drain_probe.cu measures
+// the slice in isolation at 28-30 cycles). Packed 16-bit integer maxima (VIMNMX3.U16x2, same issue rate) halve that, if an
+// accumulator word carries an INTEGER in its low half. It does when the accumulator starts from a magic constant instead of
+// zero: the draining warps write T6_MAGIC = 1.5 * 2^23 + 16512 into their columns right after reading them
+// (tcgen05.st), every UMMA accumulates, and with scale factors 2^3 * 2^3 a word ends as MAGIC + 64 * dot — exact (the
+// products are +-64, the sum stays below 2^24; tools/probe/tmem_probe.cu checks the tensor pipe on it), upper half
+// constant 0x4B40, low half = 128 * (257 - distance). tcgen05.ld.pack::16b then delivers two columns per register.
+// A group is the 8 EVEN or the 8 ODD columns of a 16-column span (the two halves of the packed registers); its key is
+// 128 * (257 - best distance) + (127 - position), position = 4 * tile + span within the warp's 64-column part, so a
+// larger key is a smaller (distance, position) and 7 bits of position cover 32 train tiles (n2 <= 7 680; larger train
+// sets take variant 1). Keys below 128 mean "no candidate" (a real key has 257 - distance >= 1).
+constexpr uint32_t T6_MAGIC = 0x4B404080u;
+constexpr uint32_t T6_MAX_TILES = 32;
+__device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
+template <bool MASKED>
+__device__ __forceinline__ void drain_span16(const uint32_t *raw, uint32_t c_first, uint32_t nvalid, uint32_t posc, uint32_t &r0,
+                                             uint32_t &r1) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = raw[i];
+        if (MASKED)
+            v[i] &= ((c_first + 2u * i < nvalid) ? 0x0000ffffu : 0u) | ((c_first + 2u * i + 1u < nvalid) ? 0xffff0000u : 0u);
+    }
+    const uint32_t key = vmax3u2(vmax3u2(v[0], v[1], v[2]), vmax3u2(v[3], v[4], v[5]), __vmaxu2(v[6], v[7])) + posc;
+    const uint32_t t = __vminu2(r0, key);
+    r0 = __vmaxu2(r0, key);
+    r1 = __vmaxu2(r1, t);
+}
+// 16-bit key -> the fix kernel's group key (distance << 22 | first column of the group); part_c0 = first column of the part
+__device__ __forceinline__ uint32_t t6_group_key(uint32_t key16, uint32_t part_c0, uint32_t parity) {
+    if (key16 < 128u) return 0xffffffffu;
+    const uint32_t pos = 127u - (key16 & 127u);
+    const uint32_t col = (pos >> 2) * (uint32_t)T4_NCOLS + part_c0 + (pos & 3u) * 16u + parity;
+    return ((257u - (key16 >> 7)) << KNN_IDX_BITS) | col;
+}
+
 // DRAIN selects how a draining warp moves its 64-column part of an accumulator out of TMEM:
 //   0  the whole part in one go (two x32 loads), accumulator handed back, then the max trees — TMEM reads (480 clk per
 //      accumulator at 64 B/clk per scheduler) and ALU work (420 clk) of a step run one after the other.
@@ -338,7 +377,7 @@ constexpr int T4_THREADS_WIDE = 128 + 32 * 24;
 // instead of the lowest: the warp arbiter of a scheduler prefers the highest warp id among eligible warps, and the one thread
 // that issues the UMMAs shares its scheduler with four draining warps that almost always have an instruction ready.
 template <int DRAIN, bool SVC_HI = false>
-__global__ void __launch_bounds__(DRAIN == 4 ? T4_THREADS_WIDE : TC_THREADS, 1)
+__global__ void __launch_bounds__((DRAIN == 4 || DRAIN == 5) ? T4_THREADS_WIDE : TC_THREADS, 1) __maxnreg__(DRAIN == 6 ? 72 : 128)
 k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
            uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -350,7 +389,9 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                    bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES;
 
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t NDW = (DRAIN == 4) ? 24u : 16u;   // draining warps
+    __shared__ uint32_t s_cst[16];
+    if (DRAIN == 6 && threadIdx.x < 16) s_cst[threadIdx.x] = T6_MAGIC;   // read back after the first __syncthreads
+    constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5) ? 24u : 16u;   // draining warps
     // role index: 0..3 = service warps, 4.. = draining warps ((wid + 4) & 3 == wid & 3, so the TMEM lane quadrant is unchanged)
     const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
     const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
@@ -365,7 +406,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
+            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : DRAIN == 5 ? 12 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
@@ -379,7 +420,18 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
-    if (warp >= 4 && warp < 8) tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), 0x86868686u);   // ue8m0 2^7 everywhere
+    if (warp >= 4 && warp < 8)   // ue8m0 2^7 everywhere (packed drain: 2^3, products are +-64)
+        tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), DRAIN == 6 ? 0x82828282u : 0x86868686u);
+    if (DRAIN == 6 && warp >= 4) {   // both accumulators start from the magic constant
+        const uint32_t cp = (warp - 4) >> 2, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + cp * 64u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            tmem_st32_const_async(t0 + h * T4_NCOLS, T6_MAGIC);
+            if (cp != 3) tmem_st32_const_async(t0 + h * T4_NCOLS + 32, T6_MAGIC);
+            else tmem_st16_const(t0 + h * T4_NCOLS + 32, T6_MAGIC);
+        }
+        tmem_wait_st();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -425,7 +477,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                         for (int k = 0; k < 4; k++) {   // 4 K-steps of 64 e2m1 (32 B) in the 128-byte row
                             const uint64_t ad = smem_desc_sw128(sA + h * 128 * T4_ROWBYTES + k * 32);
                             const uint64_t bd = smem_desc_sw128(bbase + k * 32);
-                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, k != 0 ? 1u : 0u);
+                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, (DRAIN == 6 || k != 0 || (dbg & 8)) ? 1u : 0u);
                         }
                         umma_commit(bar_tfull + 8 * h);
                     }
@@ -570,6 +622,147 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                                                     : 0xffffffffu;
                     }
                     part[((size_t)p * 2 + halfc) * n1 + q] = make_uint2(out[0], out[1]);
+                }
+            }
+        } else if (DRAIN == 5) {
+            // Variant 3's dedicated warps with 24 draining warps: on every scheduler three warps serve accumulator 0 and three
+            // accumulator 1, each taking 80 of its accumulator's 240 columns as five 16-column slices through two rotating
+            // buffers. The two groups run half a step apart (their accumulators fill half a step apart), so one group's
+            // barrier wait and first TMEM load fall into the other group's reduction; with two warps per group (variant 3)
+            // the scheduler had too little independent work while one group waited.
+            const uint32_t acc = (ew >> 2) & 1u, third = ew >> 3;          // which accumulator, which 80-column third
+            const uint32_t hc0 = third * 80u;
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+            const uint32_t taddr = acc0 + ((quad * 32u) << 16) + acc * T4_NCOLS + hc0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + acc * 128 + quad * 32 + lane;
+                float r0 = TC_KEY_NONE, r1 = TC_KEY_NONE;
+                float tbase = (float)hc0 + TC_KEY_BIAS;
+                for (uint32_t j = 0; j < ntiles; j++, g++, tbase += (float)T4_NCOLS) {
+                    const uint32_t tile0 = j * T4_NCOLS + hc0;
+                    const bool dead = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + 80u > n2;
+                    const uint32_t nvalid = dead ? 0 : n2 - tile0;
+                    mbar_wait(bar_tfull + 8 * acc, g & 1);
+                    tc_fence_after();
+                    if (dead) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        continue;
+                    }
+#define VB_SLICE(C, BUF, NEXT_LD)                                                                   \
+                    tmem_wait_ld_regs16(BUF);                                                       \
+                    NEXT_LD;                                                                        \
+                    if (masked) drain_chunk<C, true, 16>(BUF, nvalid, tbase, r0, r1);               \
+                    else drain_chunk<C, false, 16>(BUF, nvalid, tbase, r0, r1);
+                    tmem_ld16(taddr, ra);
+                    VB_SLICE(0, ra, tmem_ld16(taddr + 16, rb))
+                    VB_SLICE(16, rb, tmem_ld16(taddr + 32, ra))
+                    VB_SLICE(32, ra, tmem_ld16(taddr + 48, rb))
+                    VB_SLICE(48, rb, tmem_ld16(taddr + 64, ra))
+                    // the accumulator goes back once the last slice has landed
+                    tmem_wait_ld_regs16(ra);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (masked) drain_chunk<64, true, 16>(ra, nvalid, tbase, r0, r1);
+                    else drain_chunk<64, false, 16>(ra, nvalid, tbase, r0, r1);
+#undef VB_SLICE
+                }
+                if (q < n1) {
+                    uint32_t out[2];
+                    const float ks[2] = {r0, r1};
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint32_t ki = __float2uint_rz(ks[i]);
+                        out[i] = ks[i] < 16777216.f ? ((ki >> (TC_KEY_SHIFT + 1)) << KNN_IDX_BITS) | (ki & (TC_MAX_TRAIN - 1u))
+                                                    : 0xffffffffu;
+                    }
+                    part[((size_t)p * 3 + third) * n1 + q] = make_uint2(out[0], out[1]);
+                }
+            }
+        } else if (DRAIN == 6) {
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);   // columns [0, 32) of the part, two per register
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);   // columns [32, 64) (narrow part: [16, 48))
+            const uint32_t lane_base = acc0 + ((quad * 32u) << 16) + c0;
+            const uint32_t b_off = wide ? 32u : 16u;
+            // the constant, 8 times, read through volatile shared-memory loads: values ptxas cannot re-create, so the vector
+            // stays in 8 registers (a known constant is rebuilt with moves in front of every store)
+            uint32_t cst[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) cst[i] = *reinterpret_cast<volatile uint32_t *>(&s_cst[i]);
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
+                uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};   // per row half: packed (odd-column group, even-column group) keys
+                uint32_t posc = 127u * 0x00010001u;
+                for (uint32_t j = 0; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
+                    const uint32_t tile0 = j * T4_NCOLS + c0;
+                    const bool skip = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + cw > n2;
+                    const uint32_t nvalid = skip ? 0 : n2 - tile0;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t taddr = lane_base + h * T4_NCOLS;
+                        mbar_wait(bar_tfull + 8 * h, g & 1);
+                        tc_fence_after();
+                        if (!skip) {
+                            tmem_ld32_pack16(taddr, ra);
+                            tmem_ld32_pack16(taddr + b_off, rb);
+                            tmem_wait_ld_regs16(ra);
+                        }
+                        if (!(dbg & 16)) {   // (dbg 16: timing without the stores, results invalid)
+                            tmem_st8(taddr, cst);   // the next tile accumulates onto the constant again
+                            tmem_st8(taddr + 8, cst);
+                            tmem_st8(taddr + 16, cst);
+                            tmem_st8(taddr + 24, cst);
+                        }
+                        if (!skip) tmem_wait_ld_regs16(rb);
+                        if (!(dbg & 16)) {
+                            tmem_st8(taddr + 32, cst);
+                            tmem_st8(taddr + 40, cst);
+                            if (wide) {
+                                tmem_st8(taddr + 48, cst);
+                                tmem_st8(taddr + 56, cst);
+                            }
+                            tmem_wait_st();
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);   // handed back before anything is reduced
+                        if (skip) continue;
+                        if (masked) {
+                            drain_span16<true>(&ra[0], 0u, nvalid, posc, r0[h], r1[h]);
+                            drain_span16<true>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0[h], r1[h]);
+                        } else {
+                            drain_span16<false>(&ra[0], 0u, nvalid, posc, r0[h], r1[h]);
+                            drain_span16<false>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0[h], r1[h]);
+                        }
+                        if (wide) {
+                            if (masked) {
+                                drain_span16<true>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
+                                drain_span16<true>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0[h], r1[h]);
+                            } else {
+                                drain_span16<false>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
+                                drain_span16<false>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0[h], r1[h]);
+                            }
+                        } else {   // rb = columns [16, 48): its upper half is the part's third span
+                            if (masked) drain_span16<true>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
+                            else drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t q = qb + h * 128;
+                    if (q < n1) {
+                        // four group keys (even / odd columns x best / second): the two smallest go to the fix kernel
+                        const uint32_t ka = t6_group_key(r0[h] & 0xffffu, c0, 0u), kb = t6_group_key(r0[h] >> 16, c0, 1u);
+                        const uint32_t kc = t6_group_key(r1[h] & 0xffffu, c0, 0u), kd = t6_group_key(r1[h] >> 16, c0, 1u);
+                        const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
+                        part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(lo1, min(hi1, lo2));   // ka < kc and kb < kd
+                    }
                 }
             }
         } else if (DRAIN == 2) {
@@ -760,7 +953,11 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 //               maximum), so the second neighbour's distance is min(second smallest in the best group, the other group's
 //               key distance) without reading that group; only the second neighbour's index stays unknown (the key keeps
 //               the group's first column), and match_features (src/Frame.cpp:91-95) never looks at it. Half the bytes.
-template <int LANES>
+//   STRIDE = 2 (packed drain): a group is 8 columns of one parity, first column + 2 i. Two groups with the same best distance
+//               are ordered by first column, which orders their members too — except for the even and the odd group of ONE
+//               span, whose columns interleave: when those two tie, LANES = 8 evaluates both (the nearest neighbour is the
+//               lower index of the two groups' best members, and the second distance is then that same distance).
+template <int LANES, int STRIDE = 1>
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
                                                      size_t stride_words, uint32_t n1, uint32_t n2, uint32_t nparts,
                                                      const uint2 *__restrict__ part, uint2 *__restrict__ out) {
@@ -778,15 +975,29 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
             k1 = lo;
         }
         const uint32_t gk = (sub < 8) ? k1 : k2;
-        const uint32_t col = (gk & KNN_IDX_MASK) + (sub & 7);
+        const uint32_t col = (gk & KNN_IDX_MASK) + (sub & 7) * STRIDE;
         if (LANES == 8) other = k2;
+        const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
         if (gk != 0xffffffffu && col < n2) {
-            const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
             const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col * 8);
             const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
             const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                                __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
             key = (d << KNN_IDX_BITS) | col;
+        }
+        if (STRIDE == 2 && LANES == 8 && k2 != 0xffffffffu && (k2 >> KNN_IDX_BITS) == (k1 >> KNN_IDX_BITS) &&
+            (k2 & KNN_IDX_MASK) == (k1 & KNN_IDX_MASK) + 1u) {
+            // the odd group of the best group's span ties with it: its members interleave with the best group's
+            const uint32_t col2 = (k2 & KNN_IDX_MASK) + (sub & 7) * 2u;
+            if (col2 < n2) {
+                const uint4 *b = reinterpret_cast<const uint4 *>(d2_base + (size_t)p * stride_words + (size_t)col2 * 8);
+                const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+                const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                   __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                const uint32_t key2 = (d << KNN_IDX_BITS) | col2;
+                other = max(key, key2);   // this lane's other candidate competes for second place with its exact key
+                key = min(key, key2);
+            }
         }
     }
     uint32_t best = key;
@@ -824,6 +1035,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
@@ -835,10 +1048,15 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    // the organisations time within 3 % of each other (3 excepted); 1 needs 68 registers instead of 93,
-    // which leaves room for another submission's kernels beside the matcher (stream.cu)
-    const int drain = (int)ctx->opt("tc_drain", 1);
-    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
+    // 6 = the packed-integer drain (2.45 us per 5k x 5k pair against 2.58-2.65 for the float organisations 0-5, which time
+    // within 3 % of each other, 3 excepted). 6 and 1 are held to 72 registers, which leaves room for another
+    // submission's kernels beside the matcher (stream.cu).
+    int drain = (int)ctx->opt("tc_drain", 6);
+    // the packed drain: 7 bits of position in a 16-bit key; and when the even and the odd group of one span tie for SECOND place
+    // the group pair it hands over has the right distances but may miss the lower index — callers that want the second index
+    // (vb_knn2_hamming; match_features never looks at it) take variant 1
+    if (drain == 6 && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
+    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : drain == 5 ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
@@ -889,6 +1107,10 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc4<0, true><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 4)
         k_knn2_tc4<4><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 6)
+        k_knn2_tc4<6><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 5)
+        k_knn2_tc4<5><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 3)
         k_knn2_tc4<3><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 2)
@@ -902,8 +1124,13 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
     const bool fix8 = ctx->opt("tc_fix8", 1) != 0;
-    if (need_second_index || !fix8)
+    const bool stride2 = fp4 && drain == 6;
+    if ((need_second_index || !fix8) && stride2)
+        k_knn2_tc_fix<16, 2><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+    else if (need_second_index || !fix8)
         k_knn2_tc_fix<16><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+    else if (stride2)
+        k_knn2_tc_fix<8, 2><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     else
         k_knn2_tc_fix<8><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     ctx->prof_end("knnfix");

@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "pairs_dev.cuh"
 
 namespace vb {
 int pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nframes, uint32_t k, uint32_t bytes,
@@ -81,7 +82,7 @@ struct MultiTicket {
 
 struct vb_multi {
     std::vector<vb::Worker *> workers;
-    vb::MultiTicket tickets[2];
+    vb::MultiTicket tickets[vb::PAIRS_DEPTH];
     int next_ticket = 0;
 };
 
@@ -129,8 +130,8 @@ int vb_multi_pairs_submit(vb_multi *m, const float *pts, const uint8_t *desc, ui
                           const vb_pair_params *params, vb_pair_result *results, uint32_t *match_offsets, uint16_t *matches16,
                           uint64_t cap_matches, int *ticket) {
     VB_REQUIRE(m && pts && desc && params && results && ticket, VB_ERR_INVALID, "NULL argument");
-    MultiTicket &t = m->tickets[m->next_ticket & 1];
-    VB_REQUIRE(!t.live, VB_ERR_CAPACITY, "two submissions are already in flight: vb_multi_pairs_wait the older ticket first");
+    MultiTicket &t = m->tickets[m->next_ticket % PAIRS_DEPTH];
+    VB_REQUIRE(!t.live, VB_ERR_CAPACITY, "three submissions are already in flight: vb_multi_pairs_wait the oldest ticket first");
     const uint32_t P = nframes < 2 ? 0 : nframes - 1, nw = (uint32_t)m->workers.size();
     // every range keeps its matches in its own [first * k, (first + count) * k) window of matches16, so the window a GPU
     // writes is known before any GPU has finished
@@ -169,7 +170,7 @@ int vb_multi_pairs_submit(vb_multi *m, const float *pts, const uint8_t *desc, ui
 
 int vb_multi_pairs_wait(vb_multi *m, int ticket, uint64_t *total_matches) {
     VB_REQUIRE(m && ticket >= 0, VB_ERR_INVALID, "unknown ticket");
-    MultiTicket &t = m->tickets[ticket & 1];
+    MultiTicket &t = m->tickets[ticket % PAIRS_DEPTH];
     VB_REQUIRE(t.live, VB_ERR_INVALID, "unknown or already completed ticket");
     t.live = false;
     const uint32_t nw = (uint32_t)m->workers.size();

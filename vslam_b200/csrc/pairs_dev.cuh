@@ -6,6 +6,7 @@
 namespace vb {
 
 constexpr uint32_t PAIRS_MAX_BATCH = 1024;   // pairs per launch sequence (workspaces are sized for this)
+constexpr int PAIRS_DEPTH = 3;               // submissions in flight per context: one uploading, two computing (ctx + twin)
 
 // match_features (reference src/Frame.cpp:82-105) for P pairs whose inputs are already on the device. Pair i reads
 // p1_base + i * pts_stride / d1_base + i * desc_stride_words as frame 1 and the *2* bases as frame 2, samples with

@@ -39,7 +39,7 @@ struct PairSlot {
 };
 
 struct PairsStream {
-    PairSlot slot[2];
+    PairSlot slot[PAIRS_DEPTH];
     int next_ticket = 0;
 };
 
@@ -128,8 +128,8 @@ int pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     VB_CUDA(cudaSetDevice(ctx->device));
     PairsStream *ps = stream_state(ctx);
     VB_REQUIRE(ps != nullptr, VB_ERR_CUDA, "out of host memory");
-    PairSlot &s = ps->slot[ps->next_ticket & 1];
-    VB_REQUIRE(!s.busy, VB_ERR_CAPACITY, "two submissions are already in flight: vb_pairs_wait the older ticket first");
+    PairSlot &s = ps->slot[ps->next_ticket % PAIRS_DEPTH];
+    VB_REQUIRE(!s.busy, VB_ERR_CAPACITY, "three submissions are already in flight: vb_pairs_wait the oldest ticket first");
     const uint32_t P = nframes < 2 ? 0 : nframes - 1;
     VB_REQUIRE(base + (uint64_t)P * k <= 0xffffffffull, VB_ERR_INVALID, "match offsets are 32-bit: too many pairs x keypoints");
     s.P = P; s.base = base; s.cap = cap; s.results = results; s.offsets = match_offsets; s.matches16 = matches16;
@@ -205,7 +205,7 @@ int pairs_wait(vb_ctx *ctx, int ticket, uint64_t *total_matches) {
     VB_REQUIRE(ctx != nullptr, VB_ERR_INVALID, "ctx is NULL");
     PairsStream *ps = static_cast<PairsStream *>(ctx->pairs_stream);
     VB_REQUIRE(ps != nullptr && ticket >= 0, VB_ERR_INVALID, "unknown ticket");
-    PairSlot &s = ps->slot[ticket & 1];
+    PairSlot &s = ps->slot[ticket % PAIRS_DEPTH];
     VB_REQUIRE(s.busy && s.ticket == ticket, VB_ERR_INVALID, "unknown or already completed ticket");
     VB_CUDA(cudaSetDevice(ctx->device));
     s.busy = false;
@@ -253,8 +253,8 @@ int pairs_submit_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     VB_CUDA(cudaSetDevice(ctx->device));
     PairsStream *ps = stream_state(ctx);
     VB_REQUIRE(ps != nullptr, VB_ERR_CUDA, "out of host memory");
-    PairSlot &s = ps->slot[ps->next_ticket & 1];
-    VB_REQUIRE(!s.busy, VB_ERR_CAPACITY, "two submissions are already in flight: vb_pairs_wait the older ticket first");
+    PairSlot &s = ps->slot[ps->next_ticket % PAIRS_DEPTH];
+    VB_REQUIRE(!s.busy, VB_ERR_CAPACITY, "three submissions are already in flight: vb_pairs_wait the oldest ticket first");
     const uint32_t P = nframes < 2 ? 0 : nframes - 1;
     s.P = P; s.base = 0; s.cap = 0; s.results = nullptr; s.offsets = nullptr; s.matches16 = nullptr;
     s.ticket = ps->next_ticket;
