@@ -387,7 +387,7 @@ def main():
                 "hypotheses_decided_per_s": args.hyps * P_prof / (score_ms_avg * 1e-3),
                 "logical_GBps_full_pass_equivalent": (16.0 * evals) / (score_ms_avg * 1e-3) / 1e9,
                 "hbm_peak_GBps": peak,
-                "dram_traffic_full_count_kernel": ncu_traffic("k_count", P_prof, k, args.hyps),
+                "dram_traffic_k_count_queue": ncu_traffic("k_count", P_prof, k, args.hyps),
                 "note": "a hypothesis is abandoned only when its count so far plus every match it has not seen is below a "
                         "count another hypothesis is known to reach: winner, count, score and mask are bit-identical to "
                         "counting everything (tests/test_gpu_bounded_count.py); option ransac_prune = 0 runs the full count "

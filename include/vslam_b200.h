@@ -63,7 +63,7 @@ int vb_synchronize(vb_ctx *ctx);
  *   prune_first_chunks, prune_first16, prune_growth16, prune_rounds, prune_item_chunks   its checkpoint schedule
  *   count_packed 0, score_packed 0   scalar-instruction versions of the counting / scoring kernels
  *   kd_lanes_per_query 1/8/32        k-d tree 1-NN: lanes that share one query (A/B of the thread-per-query mapping)
- *   tc_drain 0..4, tc_svc_hi 0/1     organisation of the tensor matcher's drain / placement of its service warps
+ *   tc_drain 0..7 (default 6), tc_svc_hi 0/1     organisation of the tensor matcher's drain / placement of its service warps
  *   pairs_overlap 0                  vb_pairs_submit[_d]: every submission on one compute stream instead of alternating two
  * A build with -DVB_TUNING adds timing-only options (tc_dbg, prune_ctas_per_sm, pairs_twin, pairs_split). Unknown names
  * return VB_ERR_INVALID. vb_reset_options restores every built-in rule. */

@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
 // larger key is a smaller (distance, position) and 7 bits of position cover 32 train tiles (n2 <= 7 680; larger train
 // sets take variant 1). Keys below 128 mean "no candidate" (a real key has 257 - distance >= 1).
 constexpr uint32_t T6_MAGIC = 0x4B404080u;
-constexpr uint32_t T6_MAX_TILES = 32;
+constexpr uint32_t T6_MAX_TILES = 32;   // 4 spans per part (variant 6)
+constexpr uint32_t T7_MAX_TILES = 25;   // 5 spans per part (variant 7)
 __device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
 template <bool MASKED>
 __device__ __forceinline__ void drain_span16(const uint32_t *raw, uint32_t c_first, uint32_t nvalid, uint32_t posc, uint32_t &r0,
@@ -356,10 +357,11 @@ __device__ __forceinline__ void drain_span16(const uint32_t *raw, uint32_t c_fir
     r1 = __vmaxu2(r1, t);
 }
 // 16-bit key -> the fix kernel's group key (distance << 22 | first column of the group); part_c0 = first column of the part
+template <uint32_t SPANS = 4>   // spans per part: position = SPANS * tile + span
 __device__ __forceinline__ uint32_t t6_group_key(uint32_t key16, uint32_t part_c0, uint32_t parity) {
     if (key16 < 128u) return 0xffffffffu;
     const uint32_t pos = 127u - (key16 & 127u);
-    const uint32_t col = (pos >> 2) * (uint32_t)T4_NCOLS + part_c0 + (pos & 3u) * 16u + parity;
+    const uint32_t col = (pos / SPANS) * (uint32_t)T4_NCOLS + part_c0 + (pos % SPANS) * 16u + parity;
     return ((257u - (key16 >> 7)) << KNN_IDX_BITS) | col;
 }
 
@@ -377,7 +379,7 @@ constexpr int T4_THREADS_WIDE = 128 + 32 * 24;
 // instead of the lowest: the warp arbiter of a scheduler prefers the highest warp id among eligible warps, and the one thread
 // that issues the UMMAs shares its scheduler with four draining warps that almost always have an instruction ready.
 template <int DRAIN, bool SVC_HI = false>
-__global__ void __launch_bounds__((DRAIN == 4 || DRAIN == 5) ? T4_THREADS_WIDE : TC_THREADS, 1) __maxnreg__(DRAIN == 6 ? 72 : 128)
+__global__ void __launch_bounds__((DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? T4_THREADS_WIDE : TC_THREADS, 1) __maxnreg__((DRAIN == 6 || DRAIN == 7) ? 72 : 128)
 k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
            uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -390,8 +392,8 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ uint32_t s_cst[16];
-    if (DRAIN == 6 && threadIdx.x < 16) s_cst[threadIdx.x] = T6_MAGIC;   // read back after the first __syncthreads
-    constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5) ? 24u : 16u;   // draining warps
+    if ((DRAIN == 6 || DRAIN == 7) && threadIdx.x < 16) s_cst[threadIdx.x] = T6_MAGIC;   // read back after the first __syncthreads
+    constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? 24u : 16u;   // draining warps
     // role index: 0..3 = service warps, 4.. = draining warps ((wid + 4) & 3 == wid & 3, so the TMEM lane quadrant is unchanged)
     const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
     const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
@@ -406,7 +408,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_init(bar_afree, 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : DRAIN == 5 ? 12 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
+            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : (DRAIN == 5 || DRAIN == 7) ? 12 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
@@ -421,7 +423,14 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
     if (warp >= 4 && warp < 8)   // ue8m0 2^7 everywhere (packed drain: 2^3, products are +-64)
-        tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), DRAIN == 6 ? 0x82828282u : 0x86868686u);
+        tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), (DRAIN == 6 || DRAIN == 7) ? 0x82828282u : 0x86868686u);
+    if (DRAIN == 7 && warp >= 4) {   // each warp its 80 columns of its accumulator
+        const uint32_t ew7 = warp - 4, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + ((ew7 >> 2) & 1u) * T4_NCOLS + (ew7 >> 3) * 80u;
+        tmem_st32_const_async(t0, T6_MAGIC);
+        tmem_st32_const_async(t0 + 32, T6_MAGIC);
+        tmem_st16_const(t0 + 64, T6_MAGIC);
+        tmem_wait_st();
+    }
     if (DRAIN == 6 && warp >= 4) {   // both accumulators start from the magic constant
         const uint32_t cp = (warp - 4) >> 2, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + cp * 64u;
 #pragma unroll
@@ -477,7 +486,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                         for (int k = 0; k < 4; k++) {   // 4 K-steps of 64 e2m1 (32 B) in the 128-byte row
                             const uint64_t ad = smem_desc_sw128(sA + h * 128 * T4_ROWBYTES + k * 32);
                             const uint64_t bd = smem_desc_sw128(bbase + k * 32);
-                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, (DRAIN == 6 || k != 0 || (dbg & 8)) ? 1u : 0u);
+                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, (DRAIN == 6 || DRAIN == 7 || k != 0 || (dbg & 8)) ? 1u : 0u);
                         }
                         umma_commit(bar_tfull + 8 * h);
                     }
@@ -765,6 +774,71 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                     }
                 }
             }
+        } else if (DRAIN == 7) {
+            // The packed drain with variant 5's geometry: 24 draining warps, on every scheduler three serve accumulator 0 and
+            // three accumulator 1, 80 columns (five spans) each. The float drain gained nothing from the split because its ALU
+            // work alone filled the pipe; the packed drain needs half of it, so one group's TMEM round trip (load, store of the
+            // constant, hand-back) can hide behind the other group's max trees.
+            const uint32_t acc = (ew >> 2) & 1u, third = ew >> 3;
+            const uint32_t hc0 = third * 80u;
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);            // columns [0, 32)
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);            // columns [32, 64)
+            uint32_t(&rc)[8] = *reinterpret_cast<uint32_t(*)[8]>(&raw0[16]);         // columns [64, 80)
+            uint32_t cst[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) cst[i] = *reinterpret_cast<volatile uint32_t *>(&s_cst[i]);
+            const uint32_t taddr = acc0 + ((quad * 32u) << 16) + acc * T4_NCOLS + hc0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, q = (u % qblocks) * TC_QROWS + acc * 128 + quad * 32 + lane;
+                uint32_t r0 = 0u, r1 = 0u;
+                uint32_t posc = 127u * 0x00010001u;
+                for (uint32_t j = 0; j < ntiles; j++, g++, posc -= 5u * 0x00010001u) {
+                    const uint32_t tile0 = j * T4_NCOLS + hc0;
+                    const bool skip = (dbg & 2) || tile0 >= n2;
+                    const bool masked = tile0 + 80u > n2;
+                    const uint32_t nvalid = skip ? 0 : n2 - tile0;
+                    mbar_wait(bar_tfull + 8 * acc, g & 1);
+                    tc_fence_after();
+                    if (!skip) {
+                        tmem_ld32_pack16(taddr, ra);
+                        tmem_ld32_pack16(taddr + 32, rb);
+                        tmem_ld16_pack16(taddr + 64, rc);
+                        tmem_wait_ld_regs16(ra);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) tmem_st8(taddr + c, cst);
+                    if (!skip) tmem_wait_ld_regs16(rb);
+#pragma unroll
+                    for (int c = 32; c < 64; c += 8) tmem_st8(taddr + c, cst);
+                    if (!skip) tmem_wait_ld_regs8(rc);
+                    tmem_st8(taddr + 64, cst);
+                    tmem_st8(taddr + 72, cst);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (skip) continue;
+                    if (masked) {
+                        drain_span16<true>(&ra[0], 0u, nvalid, posc, r0, r1);
+                        drain_span16<true>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+                        drain_span16<true>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+                        drain_span16<true>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+                        drain_span16<true>(&rc[0], 64u, nvalid, posc - 4u * 0x00010001u, r0, r1);
+                    } else {
+                        drain_span16<false>(&ra[0], 0u, nvalid, posc, r0, r1);
+                        drain_span16<false>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+                        drain_span16<false>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+                        drain_span16<false>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+                        drain_span16<false>(&rc[0], 64u, nvalid, posc - 4u * 0x00010001u, r0, r1);
+                    }
+                }
+                if (q < n1) {
+                    const uint32_t ka = t6_group_key<5>(r0 & 0xffffu, hc0, 0u), kb = t6_group_key<5>(r0 >> 16, hc0, 1u);
+                    const uint32_t kc = t6_group_key<5>(r1 & 0xffffu, hc0, 0u), kd = t6_group_key<5>(r1 >> 16, hc0, 1u);
+                    const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
+                    part[((size_t)p * 3 + third) * n1 + q] = make_uint2(lo1, min(hi1, lo2));
+                }
+            }
         } else if (DRAIN == 2) {
             // Slices as in DRAIN 1, and the pipeline also runs ACROSS steps: as soon as a step's last slice has landed the
             // accumulator goes back to the MMA warp, the first slice of the next step (the other accumulator) is requested,
@@ -1037,6 +1111,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
@@ -1055,8 +1130,9 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     // the packed drain: 7 bits of position in a 16-bit key; and when the even and the odd group of one span tie for SECOND place
     // the group pair it hands over has the right distances but may miss the lower index — callers that want the second index
     // (vb_knn2_hamming; match_features never looks at it) take variant 1
-    if (drain == 6 && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
-    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : drain == 5 ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
+    if (drain == 7 && div_up(n2, (uint32_t)T4_NCOLS) > T7_MAX_TILES) drain = 6;
+    if ((drain == 6 || drain == 7) && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
+    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : (drain == 5 || drain == 7) ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
@@ -1107,6 +1183,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc4<0, true><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 4)
         k_knn2_tc4<4><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 7)
+        k_knn2_tc4<7><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 6)
         k_knn2_tc4<6><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 5)
@@ -1124,7 +1202,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
     const bool fix8 = ctx->opt("tc_fix8", 1) != 0;
-    const bool stride2 = fp4 && drain == 6;
+    const bool stride2 = fp4 && (drain == 6 || drain == 7);
     if ((need_second_index || !fix8) && stride2)
         k_knn2_tc_fix<16, 2><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     else if (need_second_index || !fix8)

@@ -164,6 +164,12 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[1
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_pack16(uint32_t taddr, uint32_t (&v)[8]) {   // 16 columns into 8 registers
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 // registers -> TMEM: one 32-bit value into 16 consecutive columns of this warp's 32 rows; asynchronous (tmem_wait_st).
 __device__ __forceinline__ void tmem_st16_const(uint32_t taddr, uint32_t v) {
     asm volatile(
