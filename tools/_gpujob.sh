@@ -1,9 +1,6 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/r2ag_gpu_tests.log; cat gpurun_out/r2ag_gpu_tests.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-(time python bench.py) > gpurun_out/r2ag_bench.json 2> gpurun_out/r2ag_bench.err; tail -4 gpurun_out/r2ag_bench.err
-python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-400
+for v in lib lib_lbc8 lib_lbc9; do
+VB_LIB_PATH=$PWD/vslam_b200/$v/libvslam_b200.so python bench.py --quick --no-cpu-baseline > gpurun_out/r2ah_$v.json 2> gpurun_out/r2ah_$v.err; tail -1 gpurun_out/r2ah_$v.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r2ag_bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], d['ms_per_step'], 'one_stream', d['value_one_stream']['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_device_resident'], 'roof', d['roofline']['frac'])
-print('config3', d['config3']['device_resident_ms'], 'config4', d['config4']['device_resident'], d['config4']['e2e'], 'launches', d['gpu_launches'])
-print(d['kernel_ms']); print(d['clocks']); print(d['cpu_baseline'])"
+import json; d=json.loads(open('gpurun_out/r2ah_$v.json').read().strip().splitlines()[-1])
+print('$v value', round(d['value']), round(d['ms_per_step'],3), 'one_stream', round(d['value_one_stream']['ms_per_step'],3), 'score', round(d['kernel_ms']['score'],4))"
+done
