@@ -49,6 +49,25 @@ def test_compact_equals_blocking_and_oracle(ctx, oracle):
             assert np.array_equal(mc[i], o["matches"]) and np.array_equal(_bits(res_c["F"][i]), _bits(o["F"].reshape(-1)))
 
 
+def test_lone_submission_uploads_in_two_pieces(ctx):
+    """A submission with nothing else in flight and >= 512 pairs uploads in two pieces and starts on the first half early;
+    with another one in flight it stays whole. Same bits either way (pair i samples with seed0 + i wherever its batch ends)."""
+    from vslam_b200.lib import unpack_compact
+    pts, desc = synth.sequence(1300, 260, 31)          # 1 299 pairs: pieces of 649 and 650, the second one in two batches
+    prm = ctx.params(0.7, 8, 32, 10.0, 5)
+    res_b, out_b = ctx.pairs_run(pts, desc, prm)
+    res_c, off, m16 = ctx.pairs_run_compact(pts, desc, prm)                     # alone: split
+    _same(res_c, unpack_compact(res_c, off, m16), res_b, out_b)
+    small = synth.sequence(4, 260, 32)
+    from vslam_b200.lib import PAIR_RESULT_DTYPE
+    r0, o0, m0 = np.zeros(3, PAIR_RESULT_DTYPE), np.zeros(3, np.uint32), np.zeros((3 * 260, 2), np.uint16)
+    r1, o1, m1 = np.zeros(1299, PAIR_RESULT_DTYPE), np.zeros(1299, np.uint32), np.zeros((1299 * 260, 2), np.uint16)
+    t0 = ctx.pairs_submit(small[0], small[1], prm, r0, o0, m0)
+    t1 = ctx.pairs_submit(pts, desc, prm, r1, o1, m1)                           # not alone: whole
+    ctx.pairs_wait(t0); ctx.pairs_wait(t1)
+    _same(r1, unpack_compact(r1, o1, m1), res_b, out_b)
+
+
 def test_three_tickets_in_flight(ctx):
     from vslam_b200.lib import PAIR_RESULT_DTYPE, VbError, pinned_empty, unpack_compact
     seqs = [synth.sequence(5, 900, s) for s in (1, 2, 3, 4, 5)]

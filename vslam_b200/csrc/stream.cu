@@ -27,7 +27,7 @@ namespace vb {
 struct PairSlot {
     DevBuf pts, desc, res, outm, pack, offs;
     cudaStream_t s_out = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_res = nullptr, ev_m = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_in0 = nullptr, ev_done = nullptr, ev_res = nullptr, ev_m = nullptr;
     bool busy = false, device_io = false;
     vb_ctx *cx = nullptr;   // the context (stream + workspaces) this slot computes on
     uint32_t P = 0;
@@ -78,7 +78,7 @@ void pairs_stream_release(vb_ctx *ctx) {
     for (PairSlot &s : ps->slot) {
         if (s.s_out) cudaStreamSynchronize(s.s_out);
         for (DevBuf *b : {&s.pts, &s.desc, &s.res, &s.outm, &s.pack, &s.offs}) b->release();
-        for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_res, s.ev_m})
+        for (cudaEvent_t e : {s.ev_in, s.ev_in0, s.ev_done, s.ev_res, s.ev_m})
             if (e) cudaEventDestroy(e);
         if (s.s_out) cudaStreamDestroy(s.s_out);
     }
@@ -144,7 +144,7 @@ int pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
     }
     if (!s.s_out) {
         VB_CUDA(cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking));
-        for (cudaEvent_t *e : {&s.ev_in, &s.ev_done, &s.ev_res, &s.ev_m}) VB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&s.ev_in, &s.ev_in0, &s.ev_done, &s.ev_res, &s.ev_m}) VB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     if (!ctx->copy_in) {
         VB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -161,17 +161,36 @@ int pairs_submit(vb_ctx *ctx, const float *pts, const uint8_t *desc, uint32_t nf
         if ((rc = s.offs.ensure((size_t)P * sizeof(uint32_t)))) return rc;
     }
     const uint32_t W = bytes / 4;
+    // Nothing else in flight (the first submission of a run, or a caller that submits and waits): the upload is exposed, so it
+    // goes in two pieces and the first half of the pairs starts as soon as its frames are there — half the pipeline fill for
+    // one extra launch sequence. With other submissions in flight the upload hides behind their kernels and the batch stays whole.
+    bool alone = true;
+    for (const PairSlot &o : ps->slot) alone = alone && (&o == &s || !o.busy);
+    const uint32_t split = (alone && P >= 512) ? P / 2 : 0;   // pairs in the first piece
     auto enqueue = [&]() -> int {
-        VB_CUDA(cudaMemcpyAsync(s.pts.p, pts, pts_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
-        VB_CUDA(cudaMemcpyAsync(s.desc.p, desc, desc_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (split) {
+            const size_t f0 = (size_t)split + 1;   // frames the first piece needs
+            VB_CUDA(cudaMemcpyAsync(s.pts.p, pts, f0 * k * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaMemcpyAsync(s.desc.p, desc, f0 * k * bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaEventRecord(s.ev_in0, ctx->copy_in));
+            VB_CUDA(cudaMemcpyAsync(s.pts.as<uint8_t>() + f0 * k * 8, reinterpret_cast<const uint8_t *>(pts) + f0 * k * 8,
+                                    pts_bytes - f0 * k * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaMemcpyAsync(s.desc.as<uint8_t>() + f0 * k * bytes, desc + f0 * k * bytes, desc_bytes - f0 * k * bytes,
+                                    cudaMemcpyHostToDevice, ctx->copy_in));
+        } else {
+            VB_CUDA(cudaMemcpyAsync(s.pts.p, pts, pts_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+            VB_CUDA(cudaMemcpyAsync(s.desc.p, desc, desc_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
         VB_CUDA(cudaEventRecord(s.ev_in, ctx->copy_in));
-        VB_CUDA(cudaStreamWaitEvent(cx->stream, s.ev_in, 0));
+        VB_CUDA(cudaStreamWaitEvent(cx->stream, split ? s.ev_in0 : s.ev_in, 0));
         const float2 *p2 = s.pts.as<float2>();
         const uint32_t *d32 = s.desc.as<uint32_t>();
         vb_pair_result *res_d = s.res.as<vb_pair_result>();
         int2 *outm_d = matches16 ? s.outm.as<int2>() : nullptr;
-        for (uint32_t b0 = 0; b0 < P; b0 += PAIRS_MAX_BATCH) {
-            const uint32_t pb = (P - b0 < PAIRS_MAX_BATCH) ? P - b0 : PAIRS_MAX_BATCH;
+        for (uint32_t b0 = 0, pb = 0; b0 < P; b0 += pb) {
+            pb = (P - b0 < PAIRS_MAX_BATCH) ? P - b0 : PAIRS_MAX_BATCH;
+            if (split && b0 < split) pb = (split - b0 < pb) ? split - b0 : pb;
+            if (split && b0 == split) VB_CUDA(cudaStreamWaitEvent(cx->stream, s.ev_in, 0));
             int r = pairs_core(cx, pb, p2 + (size_t)b0 * k, p2 + (size_t)(b0 + 1) * k, k, d32 + (size_t)b0 * k * W,
                                d32 + (size_t)(b0 + 1) * k * W, (size_t)k * W, k, k, bytes, *params, params->seed0 + b0,
                                res_d + b0, outm_d ? outm_d + (size_t)b0 * k : nullptr);
@@ -264,7 +283,7 @@ int pairs_submit_d(vb_ctx *ctx, const float *pts_d, const uint8_t *desc_d, uint3
     if (P) {
         if (!s.s_out) {
             VB_CUDA(cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking));
-            for (cudaEvent_t *e : {&s.ev_in, &s.ev_done, &s.ev_res, &s.ev_m}) VB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            for (cudaEvent_t *e : {&s.ev_in, &s.ev_in0, &s.ev_done, &s.ev_res, &s.ev_m}) VB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         }
         if (cx != ctx) {
             VB_CUDA(cudaEventRecord(s.ev_in, ctx->stream));
