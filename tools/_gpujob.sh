@@ -1,6 +1,5 @@
-N=$1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2ap_bench_n$N.json 2> gpurun_out/r2ap_bench_n$N.err; tail -3 gpurun_out/r2ap_bench_n$N.err
+python -m pytest tests/test_gpu_bounded_count.py tests/test_gpu_parity.py -x -q -k "not tensor_path_edge" 2>&1 | tail -3
+for i in 1 2; do python bench.py --quick --no-cpu-baseline > gpurun_out/r2aq.json 2> gpurun_out/r2aq.err; tail -1 gpurun_out/r2aq.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r2ap_bench_n$N.json').read().strip().splitlines()[-1])
-print('n', d['n_gpus'], 'value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e'].get('frac_of_copy_ceiling'), d['e2e']['copy_ceiling_pairs_per_s'], d['e2e']['copy_ceiling_GBps_per_gpu'], 'multi', d.get('e2e_multi',{}).get('value'))
-print('config4', d['config4']['device_resident']['value'], d['config4']['e2e']['value'])"
+import json; d=json.loads(open('gpurun_out/r2aq.json').read().strip().splitlines()[-1])
+print('value', round(d['value']), round(d['ms_per_step'],3), 'one', round(d['value_one_stream']['ms_per_step'],3), 'score', round(d['kernel_ms']['score'],4), 'e2e', round(d['e2e']['value']))"; done
