@@ -1,8 +1,3 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/r2ar_gpu_tests.log; cat gpurun_out/r2ar_gpu_tests.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-(time python bench.py) > gpurun_out/r2ar_bench.json 2> gpurun_out/r2ar_bench.err; tail -4 gpurun_out/r2ar_bench.err
-python -c "
-import json; d=json.loads(open('gpurun_out/r2ar_bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], d['ms_per_step'], 'one_stream', d['value_one_stream']['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_device_resident'], 'roof', d['roofline']['frac'])
-print('config3', d['config3']['device_resident_ms'], 'config4', d['config4']['device_resident'], d['config4']['e2e'], 'launches', d['gpu_launches'])
-print(d['kernel_ms']); print(d['clocks']); print(d['cpu_baseline']['value'], d['e2e_blocking_call']['value'], d['e2e_pageable']['value'], d['e2e']['copy_ceiling_pairs_per_s'])"
+export VB_LIB_PATH=$PWD/vslam_b200/lib_tuning/libvslam_b200.so
+TC_DRAINS=6,8 timeout 300 python tools/tc_variants.py 2>&1 | tail -2 | tee gpurun_out/r2as_tc_variants.log
+TC_DRAINS=6,8 TC_EXTRA=tc_svc_hi=1 timeout 300 python tools/tc_variants.py 2>&1 | tail -2 | tee -a gpurun_out/r2as_tc_variants.log
