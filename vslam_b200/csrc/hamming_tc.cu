@@ -365,6 +365,83 @@ __device__ __forceinline__ uint32_t t6_group_key(uint32_t key16, uint32_t part_c
     return ((257u - (key16 >> 7)) << KNN_IDX_BITS) | col;
 }
 
+// One step (one accumulator of one tile) of the packed drain for a warp's column part. FULL = every column of the part is a
+// real train descriptor (all tiles but the last): no bounds, no branches — loads, the constant back, hand-back, max trees.
+template <bool WIDE, bool FULL>
+__device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uint32_t bar_empty_h, uint32_t parity, uint32_t lane,
+                                        uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], bool skip, bool masked,
+                                        uint32_t nvalid, uint32_t posc, uint32_t &r0, uint32_t &r1, int dbg) {
+    mbar_wait(bar_full_h, parity);
+    tc_fence_after();
+    if (FULL || !skip) {
+        tmem_ld32_pack16(taddr, ra);
+        tmem_ld32_pack16(taddr + (WIDE ? 32u : 16u), rb);   // narrow part: columns [16, 48), the upper half is its third span
+        tmem_wait_ld_regs16(ra);
+    }
+    if (FULL || !(dbg & 16)) {   // (dbg 16: timing without the stores, results invalid)
+        tmem_st8(taddr, cst);    // the next tile accumulates onto the constant again
+        tmem_st8(taddr + 8, cst);
+        tmem_st8(taddr + 16, cst);
+        tmem_st8(taddr + 24, cst);
+    }
+    if (FULL || !skip) tmem_wait_ld_regs16(rb);
+    if (FULL || !(dbg & 16)) {
+        tmem_st8(taddr + 32, cst);
+        tmem_st8(taddr + 40, cst);
+        if (WIDE) {
+            tmem_st8(taddr + 48, cst);
+            tmem_st8(taddr + 56, cst);
+        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty_h);   // handed back before anything is reduced
+    if (!FULL && skip) return;
+    if (!FULL && masked) {
+        drain_span16<true>(&ra[0], 0u, nvalid, posc, r0, r1);
+        drain_span16<true>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+        if (WIDE) {
+            drain_span16<true>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+            drain_span16<true>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+        } else {
+            drain_span16<true>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+        }
+    } else {
+        drain_span16<false>(&ra[0], 0u, nvalid, posc, r0, r1);
+        drain_span16<false>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+        if (WIDE) {
+            drain_span16<false>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+            drain_span16<false>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+        } else {
+            drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+        }
+    }
+}
+// All tiles of one unit for a warp's part: the leading full tiles through the branch-free step, the rest through the general one.
+template <bool WIDE>
+__device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t &g, uint32_t lane,
+                                        uint32_t c0, uint32_t cw, uint32_t n2, uint32_t ntiles, uint32_t nfull,
+                                        uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], uint32_t (&r0)[2],
+                                        uint32_t (&r1)[2], int dbg) {
+    uint32_t posc = 127u * 0x00010001u;
+    uint32_t j = 0;
+    for (; j < nfull; j++, g++, posc -= 4u * 0x00010001u) {
+        t6_step<WIDE, true>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, false, false, cw, posc, r0[0], r1[0], 0);
+        t6_step<WIDE, true>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, false, false, cw, posc,
+                            r0[1], r1[1], 0);
+    }
+    for (; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
+        const uint32_t tile0 = j * T4_NCOLS + c0;
+        const bool skip = (dbg & 2) || tile0 >= n2;
+        const bool masked = tile0 + cw > n2;
+        const uint32_t nvalid = skip ? 0 : n2 - tile0;
+        t6_step<WIDE, false>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc, r0[0], r1[0], dbg);
+        t6_step<WIDE, false>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc,
+                             r0[1], r1[1], dbg);
+    }
+}
+
 // DRAIN selects how a draining warp moves its 64-column part of an accumulator out of TMEM:
 //   0  the whole part in one go (two x32 loads), accumulator handed back, then the max trees — TMEM reads (480 clk per
 //      accumulator at 64 B/clk per scheduler) and ALU work (420 clk) of a step run one after the other.
@@ -695,73 +772,22 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         } else if (DRAIN == 6) {
             uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);   // columns [0, 32) of the part, two per register
             uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);   // columns [32, 64) (narrow part: [16, 48))
-            const uint32_t lane_base = acc0 + ((quad * 32u) << 16) + c0;
-            const uint32_t b_off = wide ? 32u : 16u;
+            // warp-uniform by construction; the shuffle says so to the compiler (TMEM addresses live in uniform registers)
+            const uint32_t lane_base = __shfl_sync(0xffffffffu, acc0 + ((quad * 32u) << 16) + c0, 0);
             // the constant, 8 times, read through volatile shared-memory loads: values ptxas cannot re-create, so the vector
             // stays in 8 registers (a known constant is rebuilt with moves in front of every store)
             uint32_t cst[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) cst[i] = *reinterpret_cast<volatile uint32_t *>(&s_cst[i]);
+            // tiles whose columns [c0, c0 + cw) are all real train descriptors
+            uint32_t nfull = (n2 >= c0 + cw) ? (n2 - c0 - cw) / (uint32_t)T4_NCOLS + 1u : 0u;
+            if (nfull > ntiles) nfull = ntiles;
+            if (dbg) nfull = 0;   // the timing switches live in the general step
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
                 uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};   // per row half: packed (odd-column group, even-column group) keys
-                uint32_t posc = 127u * 0x00010001u;
-                for (uint32_t j = 0; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
-                    const uint32_t tile0 = j * T4_NCOLS + c0;
-                    const bool skip = (dbg & 2) || tile0 >= n2;
-                    const bool masked = tile0 + cw > n2;
-                    const uint32_t nvalid = skip ? 0 : n2 - tile0;
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t taddr = lane_base + h * T4_NCOLS;
-                        mbar_wait(bar_tfull + 8 * h, g & 1);
-                        tc_fence_after();
-                        if (!skip) {
-                            tmem_ld32_pack16(taddr, ra);
-                            tmem_ld32_pack16(taddr + b_off, rb);
-                            tmem_wait_ld_regs16(ra);
-                        }
-                        if (!(dbg & 16)) {   // (dbg 16: timing without the stores, results invalid)
-                            tmem_st8(taddr, cst);   // the next tile accumulates onto the constant again
-                            tmem_st8(taddr + 8, cst);
-                            tmem_st8(taddr + 16, cst);
-                            tmem_st8(taddr + 24, cst);
-                        }
-                        if (!skip) tmem_wait_ld_regs16(rb);
-                        if (!(dbg & 16)) {
-                            tmem_st8(taddr + 32, cst);
-                            tmem_st8(taddr + 40, cst);
-                            if (wide) {
-                                tmem_st8(taddr + 48, cst);
-                                tmem_st8(taddr + 56, cst);
-                            }
-                            tmem_wait_st();
-                        }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);   // handed back before anything is reduced
-                        if (skip) continue;
-                        if (masked) {
-                            drain_span16<true>(&ra[0], 0u, nvalid, posc, r0[h], r1[h]);
-                            drain_span16<true>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0[h], r1[h]);
-                        } else {
-                            drain_span16<false>(&ra[0], 0u, nvalid, posc, r0[h], r1[h]);
-                            drain_span16<false>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0[h], r1[h]);
-                        }
-                        if (wide) {
-                            if (masked) {
-                                drain_span16<true>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
-                                drain_span16<true>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0[h], r1[h]);
-                            } else {
-                                drain_span16<false>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
-                                drain_span16<false>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0[h], r1[h]);
-                            }
-                        } else {   // rb = columns [16, 48): its upper half is the part's third span
-                            if (masked) drain_span16<true>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
-                            else drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0[h], r1[h]);
-                        }
-                    }
-                }
+                if (wide) t6_unit<true>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg);
+                else t6_unit<false>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t q = qb + h * 128;
