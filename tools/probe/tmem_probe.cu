@@ -25,7 +25,7 @@ constexpr uint32_t MAGIC = 0x4B400200u;   // 1.5 * 2^23 + 512
 
 // out: [0,16) plain read-back of what A wrote; [16,32) pack::16b read of the same columns (base 64); [32,48) pack read at
 // base 64 + 16; [48,64) plain read after an unpack::16b store over pre-filled cells; [64, 64+32) accumulators after the MMAs
-__global__ void __launch_bounds__(128, 1) k_semantics(uint32_t *out, int bmode) {
+__global__ void __launch_bounds__(128, 1) k_semantics(uint32_t *out, int bmode, uint32_t magic, uint32_t sfa_word, uint32_t sfb_word) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem0, sB = smem0 + 16384, bar = sB + 32768, s_tmem = bar + 8;
@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(128, 1) k_semantics(uint32_t *out, int bmode) 
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
     const uint32_t lane_base = tmem_base + ((warp * 32u) << 16);
-    tmem_st32_const(lane_base, 0x7f7f7f7fu);   // scale factors 2^0 in columns [0, 32)
+    tmem_st16_const(lane_base, sfa_word);        // scale factors of A in columns [0, 16) (default 2^0)
+    tmem_st16_const(lane_base + 16, sfb_word);   // scale factors of B in columns [16, 32)
+    wait_st();
     // ---- A: pack / unpack semantics on columns [320, 352)
     uint32_t v[16], r[16];
 #pragma unroll
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128, 1) k_semantics(uint32_t *out, int bmode) 
     if (threadIdx.x == 0) for (int j = 0; j < 16; j++) out[96 + j] = r[j];
     // ---- B: exact accumulation onto the magic constant, accumulator columns [32, 32 + 240)
 #pragma unroll
-    for (int j = 0; j < 16; j++) v[j] = MAGIC;
+    for (int j = 0; j < 16; j++) v[j] = magic;
     for (uint32_t c = 32; c < 32 + 240; c += 16) ST_X16("", lane_base + c, v);
     wait_st();
     tc_fence_before();
@@ -149,7 +151,7 @@ int main() {
     cudaFuncSetAttribute(k_semantics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     for (int bmode = 0; bmode < 3; bmode++) {
         cudaMemset(out, 0, 4096);
-        k_semantics<<<1, 128, SMEM>>>(out, bmode);
+        k_semantics<<<1, 128, SMEM>>>(out, bmode, MAGIC, 0x7f7f7f7fu, 0x7f7f7f7fu);
         cudaError_t e = cudaDeviceSynchronize();
         uint32_t h[128];
         cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
@@ -160,6 +162,31 @@ int main() {
             printf("%-50s", "plain read [336,352) after that store"); for (int j = 0; j < 16; j++) printf(" %08x", h[96 + j]); printf("\n");
         }
         printf("accumulators (magic %08x, expected magic %+d): ", MAGIC, bmode == 0 ? 8 : bmode == 1 ? -8 : 0);
+        for (int j = 0; j < 32; j++) printf(" %08x", h[64 + j]);
+        printf("\n");
+    }
+    // D: the same accumulation in the DENORMAL range: magic 0x00004080 (upper half-word zero, so that unpack::16b stores can
+    // re-arm an accumulator), scale factors 2^-71 (A) * 2^-72 (B): a product of +-1 is +-64 units of 2^-149
+    for (int bmode = 0; bmode < 3; bmode++) {
+        cudaMemset(out, 0, 4096);
+        k_semantics<<<1, 128, SMEM>>>(out, bmode, 0x00004080u, 0x38383838u, 0x37373737u);
+        cudaError_t e = cudaDeviceSynchronize();
+        uint32_t h[128];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("== denormal accumulators, B block sum %s: %s\n", bmode == 0 ? "+2" : bmode == 1 ? "-2" : "0", cudaGetErrorString(e));
+        printf("accumulators (magic 00004080, expected %08x): ", 0x4080 + (bmode == 0 ? 512 : bmode == 1 ? -512 : 0));
+        for (int j = 0; j < 32; j++) printf(" %08x", h[64 + j]);
+        printf("\n");
+    }
+    // E: equal scale factors 2^-72 * 2^-72 (no assumption on which columns hold A's and which B's): +-32 units
+    for (int bmode = 0; bmode < 2; bmode++) {
+        cudaMemset(out, 0, 4096);
+        k_semantics<<<1, 128, SMEM>>>(out, bmode, 0x00004080u, 0x37373737u, 0x37373737u);
+        cudaError_t e = cudaDeviceSynchronize();
+        uint32_t h[128];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("== denormal accumulators, equal scales, B block sum %s: %s\n", bmode == 0 ? "+2" : "-2", cudaGetErrorString(e));
+        printf("accumulators (magic 00004080, expected %08x): ", 0x4080 + (bmode == 0 ? 256 : -256));
         for (int j = 0; j < 32; j++) printf(" %08x", h[64 + j]);
         printf("\n");
     }

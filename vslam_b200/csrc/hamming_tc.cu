@@ -338,6 +338,24 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
 // larger key is a smaller (distance, position) and 7 bits of position cover 32 train tiles (n2 <= 7 680; larger train
 // sets take variant 1). Keys below 128 mean "no candidate" (a real key has 257 - distance >= 1).
 constexpr uint32_t T6_MAGIC = 0x4B404080u;
+// Timeline of one CTA (TUNING builds, tc_dbg & 32): SM clock at the hand-shake points of the UMMA thread (role 0), two draining
+// warps (1, 2) and a re-arming warp (3), per step = 2 * tile + accumulator; read back with vb_debug_tc_trace (tools/tc_trace.py).
+#ifdef VB_TUNING
+constexpr uint32_t TC_TRACE_STEPS = 128, TC_TRACE_EVENTS = 6;
+constexpr uint32_t TC_TRACE_ROLES = 18;   // 0 = UMMA thread, 1 = re-arming warp 20, 2 + ew = draining warp ew
+__device__ long long g_tc_trace[TC_TRACE_ROLES * TC_TRACE_STEPS * TC_TRACE_EVENTS];
+__device__ __forceinline__ uint32_t mbar_wait_count(uint32_t bar, uint32_t parity) {   // mbar_wait, returning the failed polls
+    uint32_t n = 0;
+    while (!vb::tc::mbar_try_wait(bar, parity)) n++;
+    return n;
+}
+#define TC_TRACE(role, step, ev)                                                                                       \
+    do {                                                                                                               \
+        if ((role) >= 0 && (step) < TC_TRACE_STEPS) g_tc_trace[((role) * TC_TRACE_STEPS + (step)) * TC_TRACE_EVENTS + (ev)] = clock64(); \
+    } while (0)
+#else
+#define TC_TRACE(role, step, ev) do { } while (0)
+#endif
 constexpr uint32_t T6_MAX_TILES = 32;   // 4 spans per part (variant 6)
 constexpr uint32_t T7_MAX_TILES = 25;   // 5 spans per part (variant 7)
 __device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
@@ -370,9 +388,12 @@ __device__ __forceinline__ uint32_t t6_group_key(uint32_t key16, uint32_t part_c
 template <bool WIDE, bool FULL>
 __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uint32_t bar_empty_h, uint32_t parity, uint32_t lane,
                                         uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], bool skip, bool masked,
-                                        uint32_t nvalid, uint32_t posc, uint32_t &r0, uint32_t &r1, int dbg) {
+                                        uint32_t nvalid, uint32_t posc, uint32_t &r0, uint32_t &r1, int dbg, int trole = -1,
+                                        uint32_t tstep = 0) {
+    TC_TRACE(trole, tstep, 0);
     mbar_wait(bar_full_h, parity);
     tc_fence_after();
+    TC_TRACE(trole, tstep, 1);
     if (FULL || !skip) {
         tmem_ld32_pack16(taddr, ra);
         tmem_ld32_pack16(taddr + (WIDE ? 32u : 16u), rb);   // narrow part: columns [16, 48), the upper half is its third span
@@ -385,6 +406,7 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
         tmem_st8(taddr + 24, cst);
     }
     if (FULL || !skip) tmem_wait_ld_regs16(rb);
+    TC_TRACE(trole, tstep, 2);
     if (FULL || !(dbg & 16)) {
         tmem_st8(taddr + 32, cst);
         tmem_st8(taddr + 40, cst);
@@ -397,6 +419,7 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty_h);   // handed back before anything is reduced
+    TC_TRACE(trole, tstep, 3);
     if (!FULL && skip) return;
     if (!FULL && masked) {
         drain_span16<true>(&ra[0], 0u, nvalid, posc, r0, r1);
@@ -417,19 +440,22 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
             drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
         }
     }
+#ifdef VB_TUNING
+    if (trole >= 0) { asm volatile("" ::"r"(r0), "r"(r1) : "memory"); TC_TRACE(trole, tstep, 4); }
+#endif
 }
 // All tiles of one unit for a warp's part: the leading full tiles through the branch-free step, the rest through the general one.
 template <bool WIDE>
 __device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t &g, uint32_t lane,
                                         uint32_t c0, uint32_t cw, uint32_t n2, uint32_t ntiles, uint32_t nfull,
                                         uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], uint32_t (&r0)[2],
-                                        uint32_t (&r1)[2], int dbg) {
+                                        uint32_t (&r1)[2], int dbg, int trole = -1) {
     uint32_t posc = 127u * 0x00010001u;
     uint32_t j = 0;
     for (; j < nfull; j++, g++, posc -= 4u * 0x00010001u) {
-        t6_step<WIDE, true>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, false, false, cw, posc, r0[0], r1[0], 0);
+        t6_step<WIDE, true>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, false, false, cw, posc, r0[0], r1[0], 0, trole, 2 * g);
         t6_step<WIDE, true>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, false, false, cw, posc,
-                            r0[1], r1[1], 0);
+                            r0[1], r1[1], 0, trole, 2 * g + 1);
     }
     for (; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
         const uint32_t tile0 = j * T4_NCOLS + c0;
@@ -439,6 +465,94 @@ __device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, 
         t6_step<WIDE, false>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc, r0[0], r1[0], dbg);
         t6_step<WIDE, false>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc,
                              r0[1], r1[1], dbg);
+    }
+}
+
+// ---- packed drain with re-arming warps (DRAIN 8, 9) -------------------------------------------------------------------------
+// In variant 6 a draining warp's step is load -> store of the constant -> wait for the store -> hand-back -> max trees, one
+// after the other, and that serial chain (not a pipe) is what a step costs. Here four more warps (one per TMEM lane quadrant)
+// do nothing but re-arm: a draining warp loads its part, says so on a "read" barrier and goes straight to its max trees;
+// the re-arming warp of the quadrant waits for that barrier, writes the constant over the quadrant's 240 columns and hands
+// the accumulator back to the UMMA warp. The store round trip runs beside the max trees instead of in front of them.
+//   8  constant 1.5 * 2^23 + 16512 as in variant 6 (full-width stores)
+//   9  constant 16512 * 2^-149 — a DENORMAL whose upper half-word is zero — with scale factors 2^-71 * 2^-72, so a product
+//      of +-1 is +-64 units of 2^-149 and the low half-word is the same integer as in variant 6; the constant then goes
+//      back with tcgen05.st.unpack::16b (two columns per register: half the store traffic). Needs the tensor pipe to
+//      accumulate denormals exactly, which tools/probe/tmem_probe.cu checks.
+constexpr uint32_t T9_MAGIC = 0x00004080u;
+constexpr int T8_THREADS = 128 + 32 * 16 + 32 * 4;
+__device__ __forceinline__ void tmem_st32_unpack16(uint32_t taddr, const uint32_t (&v)[16]) {   // 32 columns from 16 registers
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16_unpack16(uint32_t taddr, const uint32_t (&v)[16]) {   // 16 columns from 8 registers
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+template <bool WIDE, bool FULL>
+__device__ __forceinline__ void t8_step(uint32_t taddr, uint32_t bar_full_h, uint32_t bar_read_h, uint32_t parity, uint32_t lane,
+                                        uint32_t (&ra)[16], uint32_t (&rb)[16], bool skip, bool masked, uint32_t nvalid,
+                                        uint32_t posc, uint32_t &r0, uint32_t &r1, int trole = -1, uint32_t tstep = 0) {
+    TC_TRACE(trole, tstep, 0);
+    mbar_wait(bar_full_h, parity);
+    tc_fence_after();
+    TC_TRACE(trole, tstep, 1);
+    if (FULL || !skip) {
+        tmem_ld32_pack16(taddr, ra);
+        tmem_ld32_pack16(taddr + (WIDE ? 32u : 16u), rb);
+        tmem_wait_ld_regs16(ra);
+        tmem_wait_ld_regs16(rb);
+    }
+    TC_TRACE(trole, tstep, 2);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_read_h);   // the part is in registers: the quadrant's re-arming warp may overwrite it
+    TC_TRACE(trole, tstep, 3);
+    if (!FULL && skip) return;
+    if (!FULL && masked) {
+        drain_span16<true>(&ra[0], 0u, nvalid, posc, r0, r1);
+        drain_span16<true>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+        if (WIDE) {
+            drain_span16<true>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+            drain_span16<true>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+        } else {
+            drain_span16<true>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+        }
+    } else {
+        drain_span16<false>(&ra[0], 0u, nvalid, posc, r0, r1);
+        drain_span16<false>(&ra[8], 16u, nvalid, posc - 0x00010001u, r0, r1);
+        if (WIDE) {
+            drain_span16<false>(&rb[0], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+            drain_span16<false>(&rb[8], 48u, nvalid, posc - 3u * 0x00010001u, r0, r1);
+        } else {
+            drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
+        }
+    }
+#ifdef VB_TUNING
+    if (trole >= 0) { asm volatile("" ::"r"(r0), "r"(r1) : "memory"); TC_TRACE(trole, tstep, 4); }
+#endif
+}
+template <bool WIDE>
+__device__ __forceinline__ void t8_unit(uint32_t lane_base, uint32_t bar_tfull, uint32_t bar_tread, uint32_t &g, uint32_t lane,
+                                        uint32_t c0, uint32_t cw, uint32_t n2, uint32_t ntiles, uint32_t nfull,
+                                        uint32_t (&ra)[16], uint32_t (&rb)[16], uint32_t (&r0)[2], uint32_t (&r1)[2], int trole = -1) {
+    uint32_t posc = 127u * 0x00010001u;
+    uint32_t j = 0;
+    for (; j < nfull; j++, g++, posc -= 4u * 0x00010001u) {
+        t8_step<WIDE, true>(lane_base, bar_tfull, bar_tread, g & 1, lane, ra, rb, false, false, cw, posc, r0[0], r1[0], trole, 2 * g);
+        t8_step<WIDE, true>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tread + 8, g & 1, lane, ra, rb, false, false, cw, posc, r0[1], r1[1], trole, 2 * g + 1);
+    }
+    for (; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
+        const uint32_t tile0 = j * T4_NCOLS + c0;
+        const bool skip = tile0 >= n2;
+        const bool masked = tile0 + cw > n2;
+        const uint32_t nvalid = skip ? 0 : n2 - tile0;
+        t8_step<WIDE, false>(lane_base, bar_tfull, bar_tread, g & 1, lane, ra, rb, skip, masked, nvalid, posc, r0[0], r1[0]);
+        t8_step<WIDE, false>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tread + 8, g & 1, lane, ra, rb, skip, masked, nvalid, posc, r0[1], r1[1]);
     }
 }
 
@@ -455,8 +569,12 @@ constexpr int T4_THREADS_WIDE = 128 + 32 * 24;
 // SVC_HI puts the four service warps (TMA producer, UMMA issuer, TMEM allocator, spare) at the HIGHEST warp ids of the CTA
 // instead of the lowest: the warp arbiter of a scheduler prefers the highest warp id among eligible warps, and the one thread
 // that issues the UMMAs shares its scheduler with four draining warps that almost always have an instruction ready.
-template <int DRAIN, bool SVC_HI = false>
-__global__ void __launch_bounds__((DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? T4_THREADS_WIDE : TC_THREADS, 1) __maxnreg__((DRAIN == 6 || DRAIN == 7) ? 72 : 128)
+// ISSUERS = 2: the spare service warp issues the UMMAs of accumulator 1 and warp 1 those of accumulator 0. One thread's chain per
+// tile — two commits, the B-stage wait, two accumulator waits, eight UMMA issues, each a dependent long-latency operation — is
+// what a tile costs (tools/tc_trace.py: the thread never finds a barrier incomplete, and the draining warps idle 40 % of the
+// time, yet the tensor pipe is 68 % active); two threads halve it.
+template <int DRAIN, bool SVC_HI = false, int ISSUERS = 1>
+__global__ void __launch_bounds__((DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? T4_THREADS_WIDE : (DRAIN == 8 || DRAIN == 9) ? T8_THREADS : TC_THREADS, 1) __maxnreg__((DRAIN >= 6) ? 72 : 128)
 k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, uint32_t n1, uint32_t n2,
            uint32_t rowstride_q, uint32_t rowstride_t, uint32_t nunits, uint2 *__restrict__ part, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -465,16 +583,25 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t sB = smem0 + T4_A_BYTES;
     const uint32_t sBar = sB + T4_STAGES * T4_B_BYTES;
     const uint32_t bar_a = sBar, bar_afree = sBar + 8, bar_tfull = sBar + 16, bar_tempty = sBar + 32, s_tmem = sBar + 48,
-                   bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES;
+                   bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES, bar_tread = sBar + 64 + 16 * T4_STAGES;
+    static_assert(64 + 16 * T4_STAGES + 16 <= 256, "barrier block");
+    constexpr bool REARM = DRAIN == 8 || DRAIN == 9;
+    constexpr uint32_t MAGIC = DRAIN == 9 ? T9_MAGIC : T6_MAGIC;
 
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ uint32_t s_cst[16];
-    if ((DRAIN == 6 || DRAIN == 7) && threadIdx.x < 16) s_cst[threadIdx.x] = T6_MAGIC;   // read back after the first __syncthreads
+    // read back after the first __syncthreads (variant 9 stores two columns per register)
+    if (DRAIN >= 6 && threadIdx.x < 16) s_cst[threadIdx.x] = DRAIN == 9 ? (T9_MAGIC | (T9_MAGIC << 16)) : T6_MAGIC;
     constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? 24u : 16u;   // draining warps
     // role index: 0..3 = service warps, 4.. = draining warps ((wid + 4) & 3 == wid & 3, so the TMEM lane quadrant is unchanged)
     const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
     const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
     const uint32_t ntiles = (n2 + T4_NCOLS - 1) / T4_NCOLS;
+#ifdef VB_TUNING
+    const int trole = ((dbg & 32) && blockIdx.x == 0 && lane == 0) ? (warp == 1 ? 0 : warp == 20 ? 1 : (warp >= 4 && warp < 20) ? (int)warp - 2 : -1) : -1;
+#else
+    constexpr int trole = -1;
+#endif
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -482,14 +609,15 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
     if (warp == 1 && lane == 0) {
         mbar_init(bar_a, 1);
-        mbar_init(bar_afree, 1);
+        mbar_init(bar_afree, ISSUERS);
         for (int s = 0; s < 2; s++) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, DRAIN == 3 ? 8 : (DRAIN == 5 || DRAIN == 7) ? 12 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining warps per accumulator
+            mbar_init(bar_tempty + 8 * s, REARM ? 4 : DRAIN == 3 ? 8 : (DRAIN == 5 || DRAIN == 7) ? 12 : DRAIN == 4 ? 24 : 4 * T4_PARTS);   // draining (re-arming) warps per accumulator
+            if (REARM) mbar_init(bar_tread + 8 * s, 4 * T4_PARTS);
         }
         for (int s = 0; s < T4_STAGES; s++) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, ISSUERS);
         }
         fence_barrier_init();
     }
@@ -499,8 +627,15 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
-    if (warp >= 4 && warp < 8)   // ue8m0 2^7 everywhere (packed drain: 2^3, products are +-64)
-        tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), (DRAIN == 6 || DRAIN == 7) ? 0x82828282u : 0x86868686u);
+    if (warp >= 4 && warp < 8) {   // ue8m0 2^7 everywhere (packed drain: 2^3, products are +-64)
+        if (DRAIN == 9) {          // A's factors (columns [0, 16)) 2^-71, B's ([16, 32)) 2^-72: products are +-64 * 2^-149
+            tmem_st16_const(tmem_base + (((warp & 3) * 32u) << 16), 0x38383838u);
+            tmem_st16_const(tmem_base + (((warp & 3) * 32u) << 16) + 16u, 0x37373737u);
+            tmem_wait_st();
+        } else {
+            tmem_st32_const(tmem_base + (((warp & 3) * 32u) << 16), DRAIN >= 6 ? 0x82828282u : 0x86868686u);
+        }
+    }
     if (DRAIN == 7 && warp >= 4) {   // each warp its 80 columns of its accumulator
         const uint32_t ew7 = warp - 4, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + ((ew7 >> 2) & 1u) * T4_NCOLS + (ew7 >> 3) * 80u;
         tmem_st32_const_async(t0, T6_MAGIC);
@@ -508,13 +643,13 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         tmem_st16_const(t0 + 64, T6_MAGIC);
         tmem_wait_st();
     }
-    if (DRAIN == 6 && warp >= 4) {   // both accumulators start from the magic constant
+    if ((DRAIN == 6 || REARM) && warp >= 4 && warp < 20) {   // both accumulators start from the magic constant
         const uint32_t cp = (warp - 4) >> 2, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + cp * 64u;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            tmem_st32_const_async(t0 + h * T4_NCOLS, T6_MAGIC);
-            if (cp != 3) tmem_st32_const_async(t0 + h * T4_NCOLS + 32, T6_MAGIC);
-            else tmem_st16_const(t0 + h * T4_NCOLS + 32, T6_MAGIC);
+            tmem_st32_const_async(t0 + h * T4_NCOLS, MAGIC);
+            if (cp != 3) tmem_st32_const_async(t0 + h * T4_NCOLS + 32, MAGIC);
+            else tmem_st16_const(t0 + h * T4_NCOLS + 32, MAGIC);
         }
         tmem_wait_st();
     }
@@ -537,39 +672,93 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                 for (uint32_t j = 0; j < ntiles; j++, g++) {
                     const uint32_t s = g % T4_STAGES, ph = (g / T4_STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    if ((dbg & 4) && g >= T4_STAGES) {   // timing floor without the B traffic (results invalid): stages keep their first tile
+                        mbar_arrive(bar_full + 8 * s);
+                        continue;
+                    }
                     mbar_expect_tx(bar_full + 8 * s, T4_B_BYTES);
                     tma_load_2d(sB + s * T4_B_BYTES, &map_t, 0, trow + (int32_t)(j * T4_NCOLS), bar_full + 8 * s);
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == 1 || (ISSUERS == 2 && warp == 3)) {
+        // The whole warp walks the loop and waits on the barriers (warp-uniform control flow); one elected lane issues.
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc_mxf4(128, T4_NCOLS);
             const uint32_t sfa = tmem_base, sfb = tmem_base + 16;
+            const int hmine = warp == 3 ? 1 : 0;   // ISSUERS == 2: this warp's accumulator
+#ifdef VB_TUNING
+            const int mrole = (ISSUERS == 2 && warp == 3) ? -1 : trole;
+#else
+            constexpr int mrole = -1;
+#endif
             uint32_t g = 0, ul = 0;
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
                 mbar_wait(bar_a, ul & 1);
                 tc_fence_after();
                 for (uint32_t j = 0; j < ntiles; j++, g++) {
                     const uint32_t s = g % T4_STAGES, ph = (g / T4_STAGES) & 1;
+                    TC_TRACE(mrole, 2 * g, 3);
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
+                    TC_TRACE(mrole, 2 * g, 4);
                     const uint32_t bbase = sB + s * T4_B_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
+                        if (ISSUERS == 2 && h != hmine) continue;
+                        TC_TRACE(mrole, 2 * g + h, 0);
                         mbar_wait(bar_tempty + 8 * h, (g & 1) ^ 1);
                         tc_fence_after();
+                        TC_TRACE(mrole, 2 * g + h, 1);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {   // 4 K-steps of 64 e2m1 (32 B) in the 128-byte row
-                            const uint64_t ad = smem_desc_sw128(sA + h * 128 * T4_ROWBYTES + k * 32);
-                            const uint64_t bd = smem_desc_sw128(bbase + k * 32);
-                            umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, (DRAIN == 6 || DRAIN == 7 || k != 0 || (dbg & 8)) ? 1u : 0u);
+                            for (int k = 0; k < 4; k++) {   // 4 K-steps of 64 e2m1 (32 B) in the 128-byte row
+                                const uint64_t ad = smem_desc_sw128(sA + h * 128 * T4_ROWBYTES + k * 32);
+                                const uint64_t bd = smem_desc_sw128(bbase + k * 32);
+                                umma_mxf4(acc0 + h * T4_NCOLS, ad, bd, idesc, sfa, sfb, (DRAIN >= 6 || k != 0 || (dbg & 8)) ? 1u : 0u);
+                            }
+                            umma_commit(bar_tfull + 8 * h);
                         }
-                        umma_commit(bar_tfull + 8 * h);
+                        TC_TRACE(mrole, 2 * g + h, 2);
                     }
-                    umma_commit(bar_empty + 8 * s);
+                    if (leader) umma_commit(bar_empty + 8 * s);
                 }
-                umma_commit(bar_afree);
+                if (leader) umma_commit(bar_afree);
+            }
+        }
+    } else if (REARM && warp >= 20) {
+        // re-arming warps, one per TMEM lane quadrant: when the quadrant's four draining warps have an accumulator in registers
+        // the constant goes back over its 240 columns and the accumulator returns to the UMMA warp
+        const uint32_t quad = warp & 3;
+        uint32_t cst[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) cst[i] = *reinterpret_cast<volatile uint32_t *>(&s_cst[i]);
+        const uint32_t lane_base = __shfl_sync(0xffffffffu, acc0 + ((quad * 32u) << 16), 0);
+        uint32_t g = 0;
+        for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (uint32_t j = 0; j < ntiles; j++, g++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t t0 = lane_base + h * T4_NCOLS;
+                    TC_TRACE(trole, 2 * g + h, 0);
+                    mbar_wait(bar_tread + 8 * h, g & 1);
+                    tc_fence_after();
+                    TC_TRACE(trole, 2 * g + h, 1);
+                    if (DRAIN == 9) {
+#pragma unroll
+                        for (int c = 0; c < 224; c += 32) tmem_st32_unpack16(t0 + c, cst);
+                        tmem_st16_unpack16(t0 + 224, cst);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 240; c += 16) tmem_st16(t0 + c, cst);
+                    }
+                    tmem_wait_st();
+                    TC_TRACE(trole, 2 * g + h, 2);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -782,12 +971,12 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             // tiles whose columns [c0, c0 + cw) are all real train descriptors
             uint32_t nfull = (n2 >= c0 + cw) ? (n2 - c0 - cw) / (uint32_t)T4_NCOLS + 1u : 0u;
             if (nfull > ntiles) nfull = ntiles;
-            if (dbg) nfull = 0;   // the timing switches live in the general step
+            if (dbg & ~(32 | 4)) nfull = 0;   // the timing switches live in the general step
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
                 uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};   // per row half: packed (odd-column group, even-column group) keys
-                if (wide) t6_unit<true>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg);
-                else t6_unit<false>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg);
+                if (wide) t6_unit<true>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
+                else t6_unit<false>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t q = qb + h * 128;
@@ -797,6 +986,28 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                         const uint32_t kc = t6_group_key(r1[h] & 0xffffu, c0, 0u), kd = t6_group_key(r1[h] >> 16, c0, 1u);
                         const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
                         part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(lo1, min(hi1, lo2));   // ka < kc and kb < kd
+                    }
+                }
+            }
+        } else if (REARM) {
+            uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);
+            uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);
+            const uint32_t lane_base = __shfl_sync(0xffffffffu, acc0 + ((quad * 32u) << 16) + c0, 0);
+            uint32_t nfull = (n2 >= c0 + cw) ? (n2 - c0 - cw) / (uint32_t)T4_NCOLS + 1u : 0u;
+            if (nfull > ntiles) nfull = ntiles;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
+                uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};
+                if (wide) t8_unit<true>(lane_base, bar_tfull, bar_tread, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, r0, r1, trole);
+                else t8_unit<false>(lane_base, bar_tfull, bar_tread, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, r0, r1, trole);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t q = qb + h * 128;
+                    if (q < n1) {
+                        const uint32_t ka = t6_group_key(r0[h] & 0xffffu, c0, 0u), kb = t6_group_key(r0[h] >> 16, c0, 1u);
+                        const uint32_t kc = t6_group_key(r1[h] & 0xffffu, c0, 0u), kd = t6_group_key(r1[h] >> 16, c0, 1u);
+                        const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
+                        part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(lo1, min(hi1, lo2));
                     }
                 }
             }
@@ -1138,6 +1349,10 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<6, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
+        VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<9, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
@@ -1157,7 +1372,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     // the group pair it hands over has the right distances but may miss the lower index — callers that want the second index
     // (vb_knn2_hamming; match_features never looks at it) take variant 1
     if (drain == 7 && div_up(n2, (uint32_t)T4_NCOLS) > T7_MAX_TILES) drain = 6;
-    if ((drain == 6 || drain == 7) && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
+    if (drain >= 6 && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
     const uint32_t nparts = fp4 ? (drain == 3 ? 2u : (drain == 5 || drain == 7) ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
@@ -1201,6 +1416,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
 #endif
     ctx->prof_begin("hamming");
     const bool svc_hi = ctx->opt("tc_svc_hi", 0) != 0;
+    const int issuers = (int)ctx->opt("tc_issuers", 1);
     if (fp4 && svc_hi && drain == 4)
         k_knn2_tc4<4, true><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && svc_hi && drain == 1)
@@ -1209,6 +1425,14 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc4<0, true><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 4)
         k_knn2_tc4<4><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 9 && issuers == 2)
+        k_knn2_tc4<9, false, 2><<<grid, T8_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 6 && issuers == 2)
+        k_knn2_tc4<6, false, 2><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 9)
+        k_knn2_tc4<9><<<grid, T8_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 8)
+        k_knn2_tc4<8><<<grid, T8_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 7)
         k_knn2_tc4<7><<<grid, T4_THREADS_WIDE, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 6)
@@ -1228,7 +1452,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
     const bool fix8 = ctx->opt("tc_fix8", 1) != 0;
-    const bool stride2 = fp4 && (drain == 6 || drain == 7);
+    const bool stride2 = fp4 && drain >= 6;
     if ((need_second_index || !fix8) && stride2)
         k_knn2_tc_fix<16, 2><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
     else if (need_second_index || !fix8)
@@ -1245,3 +1469,12 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
 }
 
 }  // namespace vb
+
+#ifdef VB_TUNING
+// TUNING builds only (not in include/vslam_b200.h): the timeline recorded by the last k_knn2_tc4 launch with tc_dbg & 32.
+extern "C" int vb_debug_tc_trace(long long *out, int n) {
+    const size_t total = sizeof(vb::g_tc_trace) / sizeof(long long);
+    if (n < 0 || (size_t)n > total) return -1;
+    return cudaMemcpyFromSymbol(out, vb::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : -2;
+}
+#endif

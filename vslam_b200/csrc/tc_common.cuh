@@ -43,6 +43,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp (elect.sync): the form ptxas recognises as "exactly one thread", so that the uniform-datapath
+// instructions underneath (UTCxMMA, UTCBAR, UTMALDG) are issued straight-line. Under a plain `if (lane == 0)` it cannot tell
+// that the branch is not divergent any further and wraps every such instruction in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
