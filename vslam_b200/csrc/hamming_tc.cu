@@ -159,40 +159,48 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
+    // Service warps walk their loops whole (warp-uniform control flow, every lane waits on the barriers) and one elected lane
+    // issues: under elect.sync ptxas emits the uniform-datapath instructions (UTMALDG, UTCxMMA, UTCBAR) straight-line.
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             uint32_t g = 0, ul = 0;   // tiles / units issued so far by this CTA
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
                 const uint32_t p = u / qblocks, q0 = (u % qblocks) * TC_QROWS;
                 const int32_t qrow = (int32_t)(p * rowstride_q + q0);
                 mbar_wait(bar_afree, (ul & 1) ^ 1);   // the previous unit's MMAs no longer read A
-                mbar_expect_tx(bar_a, TC_A_BYTES);
+                if (leader) {
+                    mbar_expect_tx(bar_a, TC_A_BYTES);
 #pragma unroll
-                for (int h = 0; h < 2; h++)
+                    for (int h = 0; h < 2; h++)
 #pragma unroll
-                    for (int kk = 0; kk < 2; kk++)
-                        tma_load_2d(sA + (h * 2 + kk) * TC_BOX_BYTES, &map_q, kk * 128, qrow + h * 128, bar_a);
+                        for (int kk = 0; kk < 2; kk++)
+                            tma_load_2d(sA + (h * 2 + kk) * TC_BOX_BYTES, &map_q, kk * 128, qrow + h * 128, bar_a);
+                }
                 const int32_t trow = (int32_t)(p * rowstride_t);
                 for (uint32_t j = 0; j < ntiles; j++, g++) {
                     const uint32_t s = g & 1, ph = (g >> 1) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     if ((dbg & 4) && g >= 2) {   // measurement only: reuse the resident stage, no L2 -> SM traffic
-                        mbar_arrive(bar_full + 8 * s);
+                        if (leader) mbar_arrive(bar_full + 8 * s);
                         continue;
                     }
-                    mbar_expect_tx(bar_full + 8 * s, TC_B_BYTES);
-                    const uint32_t dst = sB + s * TC_B_BYTES;
+                    if (leader) {
+                        mbar_expect_tx(bar_full + 8 * s, TC_B_BYTES);
+                        const uint32_t dst = sB + s * TC_B_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < 2; kk++)
+                        for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-                        for (int r = 0; r < 2; r++)
-                            tma_load_2d(dst + (kk * 2 + r) * TC_BOX_BYTES, &map_t, kk * 128,
-                                        trow + (int32_t)(j * TC_NCOLS) + r * 128, bar_full + 8 * s);
+                            for (int r = 0; r < 2; r++)
+                                tma_load_2d(dst + (kk * 2 + r) * TC_BOX_BYTES, &map_t, kk * 128,
+                                            trow + (int32_t)(j * TC_NCOLS) + r * 128, bar_full + 8 * s);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc(UMMA_FMT_E4M3, 128, TC_NCOLS);
             uint32_t g = 0, ul = 0;
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
@@ -207,19 +215,21 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                     for (int h = 0; h < 2; h++) {
                         mbar_wait(bar_tempty + 8 * h, (g & 1) ^ 1);   // accumulator h drained (previous tile)
                         tc_fence_after();
+                        if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < 2; kk++)
+                            for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const uint64_t ad = smem_desc_sw128(sA + (h * 2 + kk) * TC_BOX_BYTES + k * 32);
-                                const uint64_t bd = smem_desc_sw128(bbase + kk * 2 * TC_BOX_BYTES + k * 32);
-                                umma_f8f6f4(tmem_base + h * TC_NCOLS, ad, bd, idesc, (kk | k) != 0 ? 1u : 0u);
-                            }
-                        umma_commit(bar_tfull + 8 * h);
+                                for (int k = 0; k < 4; k++) {
+                                    const uint64_t ad = smem_desc_sw128(sA + (h * 2 + kk) * TC_BOX_BYTES + k * 32);
+                                    const uint64_t bd = smem_desc_sw128(bbase + kk * 2 * TC_BOX_BYTES + k * 32);
+                                    umma_f8f6f4(tmem_base + h * TC_NCOLS, ad, bd, idesc, (kk | k) != 0 ? 1u : 0u);
+                                }
+                            umma_commit(bar_tfull + 8 * h);
+                        }
                     }
-                    umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
+                    if (leader) umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
                 }
-                umma_commit(bar_afree);   // ... and every MMA of this unit has consumed A
+                if (leader) umma_commit(bar_afree);   // ... and every MMA of this unit has consumed A
             }
         }
     } else if (warp >= 4) {
@@ -659,25 +669,30 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t acc0 = tmem_base + T4_SF_COLS;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             uint32_t g = 0, ul = 0;
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ul++) {
                 const uint32_t p = u / qblocks, q0 = (u % qblocks) * TC_QROWS;
                 const int32_t qrow = (int32_t)(p * rowstride_q + q0);
                 mbar_wait(bar_afree, (ul & 1) ^ 1);
-                mbar_expect_tx(bar_a, T4_A_BYTES);
-                tma_load_2d(sA, &map_q, 0, qrow, bar_a);
-                tma_load_2d(sA + 128 * T4_ROWBYTES, &map_q, 0, qrow + 128, bar_a);
+                if (leader) {
+                    mbar_expect_tx(bar_a, T4_A_BYTES);
+                    tma_load_2d(sA, &map_q, 0, qrow, bar_a);
+                    tma_load_2d(sA + 128 * T4_ROWBYTES, &map_q, 0, qrow + 128, bar_a);
+                }
                 const int32_t trow = (int32_t)(p * rowstride_t);
                 for (uint32_t j = 0; j < ntiles; j++, g++) {
                     const uint32_t s = g % T4_STAGES, ph = (g / T4_STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     if ((dbg & 4) && g >= T4_STAGES) {   // timing floor without the B traffic (results invalid): stages keep their first tile
-                        mbar_arrive(bar_full + 8 * s);
+                        if (leader) mbar_arrive(bar_full + 8 * s);
                         continue;
                     }
-                    mbar_expect_tx(bar_full + 8 * s, T4_B_BYTES);
-                    tma_load_2d(sB + s * T4_B_BYTES, &map_t, 0, trow + (int32_t)(j * T4_NCOLS), bar_full + 8 * s);
+                    if (leader) {
+                        mbar_expect_tx(bar_full + 8 * s, T4_B_BYTES);
+                        tma_load_2d(sB + s * T4_B_BYTES, &map_t, 0, trow + (int32_t)(j * T4_NCOLS), bar_full + 8 * s);
+                    }
                 }
             }
         }

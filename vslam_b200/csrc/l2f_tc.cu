@@ -146,17 +146,22 @@ k_l2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUten
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
+    // Service warps walk their loops whole (every lane waits on the barriers); one elected lane issues, so that ptxas emits
+    // UTMALDG / UTCHMMA / UTCBAR straight-line instead of an ELECT / BRA.U.ANY loop around each (tc_common.cuh, elect_one).
     if (warp == 0) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        if (leader) {
             mbar_expect_tx(bar_a, Cfg::A_BYTES);
 #pragma unroll
             for (int h = 0; h < 2; h++)
 #pragma unroll
                 for (int ka = 0; ka < KATOMS; ka++)
                     tma_load_2d(sA + (h * KATOMS + ka) * LT_BOX, &map_q, ka * 64, (int32_t)(q0 + h * 128), bar_a);
-            for (uint32_t j = 0; j < ntiles; j++) {
-                const uint32_t s = j & 1, ph = (j >> 1) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        }
+        for (uint32_t j = 0; j < ntiles; j++) {
+            const uint32_t s = j & 1, ph = (j >> 1) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (leader) {
                 mbar_expect_tx(bar_full + 8 * s, Cfg::B_BYTES);
                 const uint32_t dst = sB + s * Cfg::B_BYTES;
 #pragma unroll
@@ -168,18 +173,19 @@ k_l2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUten
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(UMMA_FMT_BF16, 128, LT_NCOLS);
-            mbar_wait(bar_a, 0);
-            for (uint32_t j = 0; j < ntiles; j++) {
-                const uint32_t s = j & 1, ph = (j >> 1) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t bbase = sB + s * Cfg::B_BYTES;
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = umma_idesc(UMMA_FMT_BF16, 128, LT_NCOLS);
+        mbar_wait(bar_a, 0);
+        for (uint32_t j = 0; j < ntiles; j++) {
+            const uint32_t s = j & 1, ph = (j >> 1) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t bbase = sB + s * Cfg::B_BYTES;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    mbar_wait(bar_tempty + 8 * h, (j & 1) ^ 1);   // accumulator h drained (tile j-1)
-                    tc_fence_after();
+            for (int h = 0; h < 2; h++) {
+                mbar_wait(bar_tempty + 8 * h, (j & 1) ^ 1);   // accumulator h drained (tile j-1)
+                tc_fence_after();
+                if (leader) {
 #pragma unroll
                     for (int ka = 0; ka < KATOMS; ka++)
 #pragma unroll
@@ -190,8 +196,8 @@ k_l2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUten
                         }
                     umma_commit(bar_tfull + 8 * h);
                 }
-                umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
             }
+            if (leader) umma_commit(bar_empty + 8 * s);   // both halves have consumed this B stage
         }
     } else if (warp >= 4) {
         const uint32_t ew = warp - 4;

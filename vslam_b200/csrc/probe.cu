@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128, 1) k_probe_umma(int kind, uint32_t N, uin
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1 && lane == 0) {
+    if (warp == 1 && elect_one()) {   // warp-uniform condition, then one elected lane: straight-line UTCxMMA (tc_common.cuh)
         const uint32_t acc = tmem_base + 32, sfa = tmem_base, sfb = tmem_base + 16;
         const uint32_t idesc4 = umma_idesc_mxf4(128, N);
         const uint32_t idesc8 = umma_idesc(UMMA_FMT_E4M3, 128, N);
