@@ -348,9 +348,10 @@ __global__ void __launch_bounds__(256) k_expand_e2m1(const uint32_t *__restrict_
 // larger key is a smaller (distance, position) and 7 bits of position cover 32 train tiles (n2 <= 7 680; larger train
 // sets take variant 1). Keys below 128 mean "no candidate" (a real key has 257 - distance >= 1).
 constexpr uint32_t T6_MAGIC = 0x4B404080u;
-// Timeline of one CTA (TUNING builds, tc_dbg & 32): SM clock at the hand-shake points of the UMMA thread (role 0), two draining
+// Timeline of one CTA (builds with -DVB_TC_TRACE on top of TUNING=1, tc_dbg & 32; the trace points cost the UMMA warp time even
+// when they are switched off, so the plain TUNING build leaves them out): SM clock at the hand-shake points of the UMMA thread (role 0), two draining
 // warps (1, 2) and a re-arming warp (3), per step = 2 * tile + accumulator; read back with vb_debug_tc_trace (tools/tc_trace.py).
-#ifdef VB_TUNING
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
 constexpr uint32_t TC_TRACE_STEPS = 128, TC_TRACE_EVENTS = 6;
 constexpr uint32_t TC_TRACE_ROLES = 18;   // 0 = UMMA thread, 1 = re-arming warp 20, 2 + ew = draining warp ew
 __device__ long long g_tc_trace[TC_TRACE_ROLES * TC_TRACE_STEPS * TC_TRACE_EVENTS];
@@ -450,7 +451,7 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
             drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
         }
     }
-#ifdef VB_TUNING
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
     if (trole >= 0) { asm volatile("" ::"r"(r0), "r"(r1) : "memory"); TC_TRACE(trole, tstep, 4); }
 #endif
 }
@@ -542,7 +543,7 @@ __device__ __forceinline__ void t8_step(uint32_t taddr, uint32_t bar_full_h, uin
             drain_span16<false>(&rb[8], 32u, nvalid, posc - 2u * 0x00010001u, r0, r1);
         }
     }
-#ifdef VB_TUNING
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
     if (trole >= 0) { asm volatile("" ::"r"(r0), "r"(r1) : "memory"); TC_TRACE(trole, tstep, 4); }
 #endif
 }
@@ -607,7 +608,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
     const uint32_t qblocks = (n1 + TC_QROWS - 1) / TC_QROWS;
     const uint32_t ntiles = (n2 + T4_NCOLS - 1) / T4_NCOLS;
-#ifdef VB_TUNING
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
     const int trole = ((dbg & 32) && blockIdx.x == 0 && lane == 0) ? (warp == 1 ? 0 : warp == 20 ? 1 : (warp >= 4 && warp < 20) ? (int)warp - 2 : -1) : -1;
 #else
     constexpr int trole = -1;
@@ -703,7 +704,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             constexpr uint32_t idesc = umma_idesc_mxf4(128, T4_NCOLS);
             const uint32_t sfa = tmem_base, sfb = tmem_base + 16;
             const int hmine = warp == 3 ? 1 : 0;   // ISSUERS == 2: this warp's accumulator
-#ifdef VB_TUNING
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
             const int mrole = (ISSUERS == 2 && warp == 3) ? -1 : trole;
 #else
             constexpr int mrole = -1;
@@ -1485,8 +1486,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
 
 }  // namespace vb
 
-#ifdef VB_TUNING
-// TUNING builds only (not in include/vslam_b200.h): the timeline recorded by the last k_knn2_tc4 launch with tc_dbg & 32.
+#if defined(VB_TUNING) && defined(VB_TC_TRACE)
+// TUNING + TRACE builds only (not in include/vslam_b200.h): the timeline recorded by the last k_knn2_tc4 launch with tc_dbg & 32.
 extern "C" int vb_debug_tc_trace(long long *out, int n) {
     const size_t total = sizeof(vb::g_tc_trace) / sizeof(long long);
     if (n < 0 || (size_t)n > total) return -1;
