@@ -264,7 +264,7 @@ TC_SHAPES = [(1, 2), (1, 7), (3, 8), (5, 9), (255, 239), (256, 240), (257, 241),
              (256, 8), (300, 1000), (3000, 239), (3000, 241), (1000, 16383), (2500, 16384), (513, 720), (100, 961)]
 
 
-@pytest.mark.parametrize("drain", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("drain", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("n1,n2", TC_SHAPES)
 def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, n1, n2, drain):
     """The tcgen05 matcher (k_knn2_tc4 + k_knn2_tc_fix) forced onto shapes the size heuristic would send to the popcount
@@ -294,7 +294,7 @@ def test_knn2_hamming_tensor_path_edge_shapes(ctx, oracle, n1, n2, drain):
         assert np.array_equal(ctx.match_hamming(d1, d2, ratio), oracle.match_hamming(d1, d2, ratio))
 
 
-@pytest.mark.parametrize("drain", [6, 7, 8, 9, 106, 109])   # 100 + d: variant d with two UMMA-issuing warps (tc_issuers = 2)
+@pytest.mark.parametrize("drain", [6, 7, 8, 9, 10, 106, 109])   # 100 + d: variant d with two UMMA-issuing warps (tc_issuers = 2)
 @pytest.mark.parametrize("n2", [500, 4999, 6001, 7680, 7681])
 def test_packed_drain_interleaved_group_ties(ctx, oracle, n2, drain):
     """The packed drain (tc_drain = 6, the default) ranks groups of 8 same-parity columns of a 16-column span; the even and the
@@ -733,7 +733,7 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
 @pytest.mark.parametrize("opts", [dict(count_packed=0, score_packed=0, hamming_fp4=0), dict(tc_fix8=0), dict(hamming_qpt=1, hamming_tc=0),
                                   dict(hamming_qpt=4, hamming_tc=0), dict(tc_drain=1), dict(tc_drain=2), dict(tc_drain=3),
                                   dict(tc_drain=4), dict(tc_drain=5), dict(tc_drain=6), dict(tc_drain=7), dict(tc_drain=8), dict(tc_drain=9),
-                                  dict(tc_drain=6, tc_issuers=2)])
+                                  dict(tc_drain=10), dict(tc_drain=6, tc_issuers=2)])
 def test_alternative_kernels_agree_with_oracle(ctx, oracle, opts):
     """The code paths behind vb_set_option — k_count<2> / k_score<2> (scalar-instruction versions), the fp8 matcher, the
     two-group fix pass on the match path, the popcount matcher's queries-per-thread variants — still agree with the oracle."""

@@ -369,6 +369,20 @@ __device__ __forceinline__ uint32_t mbar_wait_count(uint32_t bar, uint32_t parit
 #endif
 constexpr uint32_t T6_MAX_TILES = 32;   // 4 spans per part (variant 6)
 constexpr uint32_t T7_MAX_TILES = 25;   // 5 spans per part (variant 7)
+__device__ __forceinline__ void tmem_st32_unpack16(uint32_t taddr, const uint32_t (&v)[16]) {   // 32 columns from 16 registers
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+template <int NREG>
+__device__ __forceinline__ void tmem_st16_unpack16(uint32_t taddr, const uint32_t (&v)[NREG]) {   // 16 columns from 8 registers
+    static_assert(NREG >= 8, "eight packed registers");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
 template <bool MASKED>
 __device__ __forceinline__ void drain_span16(const uint32_t *raw, uint32_t c_first, uint32_t nvalid, uint32_t posc, uint32_t &r0,
@@ -396,7 +410,9 @@ __device__ __forceinline__ uint32_t t6_group_key(uint32_t key16, uint32_t part_c
 
 // One step (one accumulator of one tile) of the packed drain for a warp's column part. FULL = every column of the part is a
 // real train descriptor (all tiles but the last): no bounds, no branches — loads, the constant back, hand-back, max trees.
-template <bool WIDE, bool FULL>
+// UNPACK (variant 10): the constant is the denormal of variant 9 and goes back with tcgen05.st.unpack::16b, two columns per
+// register — half the store traffic of the hand-back.
+template <bool WIDE, bool FULL, bool UNPACK = false>
 __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uint32_t bar_empty_h, uint32_t parity, uint32_t lane,
                                         uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], bool skip, bool masked,
                                         uint32_t nvalid, uint32_t posc, uint32_t &r0, uint32_t &r1, int dbg, int trole = -1,
@@ -410,7 +426,10 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
         tmem_ld32_pack16(taddr + (WIDE ? 32u : 16u), rb);   // narrow part: columns [16, 48), the upper half is its third span
         tmem_wait_ld_regs16(ra);
     }
-    if (FULL || !(dbg & 16)) {   // (dbg 16: timing without the stores, results invalid)
+    if (UNPACK) {
+        tmem_st16_unpack16(taddr, cst);
+        tmem_st16_unpack16(taddr + 16, cst);
+    } else if (FULL || !(dbg & 16)) {   // (dbg 16: timing without the stores, results invalid)
         tmem_st8(taddr, cst);    // the next tile accumulates onto the constant again
         tmem_st8(taddr + 8, cst);
         tmem_st8(taddr + 16, cst);
@@ -418,7 +437,11 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
     }
     if (FULL || !skip) tmem_wait_ld_regs16(rb);
     TC_TRACE(trole, tstep, 2);
-    if (FULL || !(dbg & 16)) {
+    if (UNPACK) {
+        tmem_st16_unpack16(taddr + 32, cst);
+        if (WIDE) tmem_st16_unpack16(taddr + 48, cst);
+        tmem_wait_st();
+    } else if (FULL || !(dbg & 16)) {
         tmem_st8(taddr + 32, cst);
         tmem_st8(taddr + 40, cst);
         if (WIDE) {
@@ -456,7 +479,7 @@ __device__ __forceinline__ void t6_step(uint32_t taddr, uint32_t bar_full_h, uin
 #endif
 }
 // All tiles of one unit for a warp's part: the leading full tiles through the branch-free step, the rest through the general one.
-template <bool WIDE>
+template <bool WIDE, bool UNPACK = false>
 __device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t &g, uint32_t lane,
                                         uint32_t c0, uint32_t cw, uint32_t n2, uint32_t ntiles, uint32_t nfull,
                                         uint32_t (&ra)[16], uint32_t (&rb)[16], const uint32_t (&cst)[8], uint32_t (&r0)[2],
@@ -464,18 +487,18 @@ __device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, 
     uint32_t posc = 127u * 0x00010001u;
     uint32_t j = 0;
     for (; j < nfull; j++, g++, posc -= 4u * 0x00010001u) {
-        t6_step<WIDE, true>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, false, false, cw, posc, r0[0], r1[0], 0, trole, 2 * g);
-        t6_step<WIDE, true>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, false, false, cw, posc,
-                            r0[1], r1[1], 0, trole, 2 * g + 1);
+        t6_step<WIDE, true, UNPACK>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, false, false, cw, posc, r0[0], r1[0], 0, trole, 2 * g);
+        t6_step<WIDE, true, UNPACK>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, false, false, cw, posc,
+                                    r0[1], r1[1], 0, trole, 2 * g + 1);
     }
     for (; j < ntiles; j++, g++, posc -= 4u * 0x00010001u) {
         const uint32_t tile0 = j * T4_NCOLS + c0;
         const bool skip = (dbg & 2) || tile0 >= n2;
         const bool masked = tile0 + cw > n2;
         const uint32_t nvalid = skip ? 0 : n2 - tile0;
-        t6_step<WIDE, false>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc, r0[0], r1[0], dbg);
-        t6_step<WIDE, false>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc,
-                             r0[1], r1[1], dbg);
+        t6_step<WIDE, false, UNPACK>(lane_base, bar_tfull, bar_tempty, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc, r0[0], r1[0], dbg);
+        t6_step<WIDE, false, UNPACK>(lane_base + T4_NCOLS, bar_tfull + 8, bar_tempty + 8, g & 1, lane, ra, rb, cst, skip, masked, nvalid, posc,
+                                     r0[1], r1[1], dbg);
     }
 }
 
@@ -492,18 +515,6 @@ __device__ __forceinline__ void t6_unit(uint32_t lane_base, uint32_t bar_tfull, 
 //      accumulate denormals exactly, which tools/probe/tmem_probe.cu checks.
 constexpr uint32_t T9_MAGIC = 0x00004080u;
 constexpr int T8_THREADS = 128 + 32 * 16 + 32 * 4;
-__device__ __forceinline__ void tmem_st32_unpack16(uint32_t taddr, const uint32_t (&v)[16]) {   // 32 columns from 16 registers
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st16_unpack16(uint32_t taddr, const uint32_t (&v)[16]) {   // 16 columns from 8 registers
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.unpack::16b.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
 template <bool WIDE, bool FULL>
 __device__ __forceinline__ void t8_step(uint32_t taddr, uint32_t bar_full_h, uint32_t bar_read_h, uint32_t parity, uint32_t lane,
                                         uint32_t (&ra)[16], uint32_t (&rb)[16], bool skip, bool masked, uint32_t nvalid,
@@ -597,12 +608,13 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                    bar_full = sBar + 64, bar_empty = sBar + 64 + 8 * T4_STAGES, bar_tread = sBar + 64 + 16 * T4_STAGES;
     static_assert(64 + 16 * T4_STAGES + 16 <= 256, "barrier block");
     constexpr bool REARM = DRAIN == 8 || DRAIN == 9;
-    constexpr uint32_t MAGIC = DRAIN == 9 ? T9_MAGIC : T6_MAGIC;
+    constexpr bool DENORM = DRAIN == 9 || DRAIN == 10;   // accumulators in the denormal range, unpack::16b stores
+    constexpr uint32_t MAGIC = DENORM ? T9_MAGIC : T6_MAGIC;
 
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ uint32_t s_cst[16];
     // read back after the first __syncthreads (variant 9 stores two columns per register)
-    if (DRAIN >= 6 && threadIdx.x < 16) s_cst[threadIdx.x] = DRAIN == 9 ? (T9_MAGIC | (T9_MAGIC << 16)) : T6_MAGIC;
+    if (DRAIN >= 6 && threadIdx.x < 16) s_cst[threadIdx.x] = DENORM ? (T9_MAGIC | (T9_MAGIC << 16)) : T6_MAGIC;
     constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? 24u : 16u;   // draining warps
     // role index: 0..3 = service warps, 4.. = draining warps ((wid + 4) & 3 == wid & 3, so the TMEM lane quadrant is unchanged)
     const uint32_t warp = SVC_HI ? (wid >= NDW ? wid - NDW : wid + 4u) : wid;
@@ -639,7 +651,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
     if (warp >= 4 && warp < 8) {   // ue8m0 2^7 everywhere (packed drain: 2^3, products are +-64)
-        if (DRAIN == 9) {          // A's factors (columns [0, 16)) 2^-71, B's ([16, 32)) 2^-72: products are +-64 * 2^-149
+        if (DENORM) {              // A's factors (columns [0, 16)) 2^-71, B's ([16, 32)) 2^-72: products are +-64 * 2^-149
             tmem_st16_const(tmem_base + (((warp & 3) * 32u) << 16), 0x38383838u);
             tmem_st16_const(tmem_base + (((warp & 3) * 32u) << 16) + 16u, 0x37373737u);
             tmem_wait_st();
@@ -654,7 +666,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         tmem_st16_const(t0 + 64, T6_MAGIC);
         tmem_wait_st();
     }
-    if ((DRAIN == 6 || REARM) && warp >= 4 && warp < 20) {   // both accumulators start from the magic constant
+    if ((DRAIN == 6 || DRAIN == 10 || REARM) && warp >= 4 && warp < 20) {   // both accumulators start from the magic constant
         const uint32_t cp = (warp - 4) >> 2, t0 = tmem_base + T4_SF_COLS + (((warp & 3) * 32u) << 16) + cp * 64u;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -974,7 +986,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                     part[((size_t)p * 3 + third) * n1 + q] = make_uint2(out[0], out[1]);
                 }
             }
-        } else if (DRAIN == 6) {
+        } else if (DRAIN == 6 || DRAIN == 10) {
             uint32_t(&ra)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw0);   // columns [0, 32) of the part, two per register
             uint32_t(&rb)[16] = *reinterpret_cast<uint32_t(*)[16]>(raw1);   // columns [32, 64) (narrow part: [16, 48))
             // warp-uniform by construction; the shuffle says so to the compiler (TMEM addresses live in uniform registers)
@@ -991,8 +1003,8 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
                 uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};   // per row half: packed (odd-column group, even-column group) keys
-                if (wide) t6_unit<true>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
-                else t6_unit<false>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
+                if (wide) t6_unit<true, DRAIN == 10>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
+                else t6_unit<false, DRAIN == 10>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t q = qb + h * 128;
@@ -1367,6 +1379,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
+        VB_CUDA(cudaFuncSetAttribute(k_knn2_tc4<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<6, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<9, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
         VB_CUDA((cudaFuncSetAttribute(k_knn2_tc4<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES)));
@@ -1380,10 +1393,11 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     int rc;
     const size_t rows_total = seq ? (size_t)(P + 1) * n1 : (size_t)P * ((size_t)n1 + n2);
     if ((rc = ctx->ws_ensure(WS_EXP, rows_total * rowbytes))) return rc;
-    // 6 = the packed-integer drain (2.45 us per 5k x 5k pair against 2.58-2.65 for the float organisations 0-5, which time
-    // within 3 % of each other, 3 excepted). 6 and 1 are held to 72 registers, which leaves room for another
-    // submission's kernels beside the matcher (stream.cu).
-    int drain = (int)ctx->opt("tc_drain", 6);
+    // 10 = the packed-integer drain on denormal accumulators, constant re-armed with unpack::16b stores (1.88 us per 5k x 5k
+    // pair; 6, the same drain on a normal-range constant with full-width stores: 1.96-2.07; the float organisations 0-5:
+    // 2.47-2.52). 6-10 and 1 are held to 72 registers, which leaves room for another submission's
+    // kernels beside the matcher (stream.cu).
+    int drain = (int)ctx->opt("tc_drain", 10);
     // the packed drain: 7 bits of position in a 16-bit key; and when the even and the odd group of one span tie for SECOND place
     // the group pair it hands over has the right distances but may miss the lower index — callers that want the second index
     // (vb_knn2_hamming; match_features never looks at it) take variant 1
@@ -1445,6 +1459,8 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
         k_knn2_tc4<9, false, 2><<<grid, T8_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 6 && issuers == 2)
         k_knn2_tc4<6, false, 2><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
+    else if (fp4 && drain == 10)
+        k_knn2_tc4<10><<<grid, TC_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 9)
         k_knn2_tc4<9><<<grid, T8_THREADS, T4_SMEM_BYTES, ctx->stream>>>(mq, mt, n1, n2, n1, n2, nunits, part, dbg);
     else if (fp4 && drain == 8)
