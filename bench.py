@@ -575,7 +575,7 @@ def hamming_roofline(P, k, ms, bf16_peak, peak_src, probe):
     fp4 = "hamming_fp4=0" not in os.environ.get("VB_OPTIONS", "")
     tf = 2.0 * 256.0 * float(P) * k * k / (ms * 1e-3) / 1e12
     peak = probe["mxf4_n240"] if fp4 else probe["f8f6f4_n256"]
-    return {"kernel": "k_knn2_tc4 (tcgen05 kind::mxf4, e2m1 +-1, ue8m0 2^7 scales)" if fp4 else
+    return {"kernel": "k_knn2_tc4<10> (tcgen05 kind::mxf4, e2m1 +-1 on denormal accumulators: ue8m0 2^-71 x 2^-72 scales, packed 16-bit drain)" if fp4 else
                       "k_knn2_tc (tcgen05 kind::f8f6f4, e4m3 +-128)",
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
             "peak_source": "measured in this run: vb_probe_tensor_peak, UMMA-only loop of the kernel's instruction shape "

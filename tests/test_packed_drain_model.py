@@ -1,4 +1,4 @@
-"""numpy model of the tensor matcher's packed drain (vslam_b200/csrc/hamming_tc.cu, tc_drain = 6) and of the stride-2 fix
+"""numpy model of the tensor matcher's packed drain (vslam_b200/csrc/hamming_tc.cu, tc_drain = 6 .. 10) and of the stride-2 fix
 pass: the ARITHMETIC of the scheme, checked on the CPU against the definition — BFMatcher(NORM_HAMMING) knnMatch k = 2
 (reference src/Frame.cpp:83-85: nearest and second nearest by (distance, train index)) and the ratio test of :91.
 
@@ -159,3 +159,27 @@ def test_packed_drain_position_range():
     d[n2 - 1] = 0
     check_row(d, n2)
     assert 128 * 257 + 127 < 65536
+
+
+def test_denormal_accumulators_carry_the_same_low_half_word():
+    """Variants 9 and 10 start an accumulator from the DENORMAL 16512 * 2^-149 (bits 0x00004080) and scale every product to
+    +-64 * 2^-149 (ue8m0 factors 2^-71 and 2^-72), so that the constant can be written back with tcgen05.st.unpack::16b, which
+    zero-fills the upper half-words. In IEEE fp32 with gradual underflow that sum is exact in any order: the bits are
+    16512 + 64 * dot, upper half-word zero, the low half-word the one variant 6 reads. (That the tensor pipe does not flush
+    denormals is checked on the GPU: tools/probe/tmem_probe.cu and every parity test of the default matcher.)"""
+    rng = np.random.default_rng(4)
+    unit = np.float32(2.0 ** -149)
+    assert unit > 0 and np.array([unit]).view(np.uint32)[0] == 1      # numpy keeps denormals
+    prod = np.float32(2.0 ** -71) * np.float32(2.0 ** -72)           # one +1 * +1 product after both scale factors
+    assert np.array([prod]).view(np.uint32)[0] == 64
+    for dist in list(range(0, 257, 16)) + [1, 255, 37, 200]:
+        bits = np.concatenate([np.ones(256 - dist, np.float32), -np.ones(dist, np.float32)])
+        rng.shuffle(bits)
+        acc = np.array([0x00004080], np.uint32).view(np.float32)[0]
+        for k in range(4):                                             # four K-steps of 64 products, each summed exactly
+            step = np.float32(bits[64 * k:64 * k + 64].sum()) * prod
+            acc = np.float32(acc + step)
+        word = int(np.array([acc]).view(np.uint32)[0])
+        ref = int(accumulate(np.array([[dist]]))[0, 0])
+        assert word >> 16 == 0 and word == 16512 + 64 * (256 - 2 * dist)
+        assert word & 0xFFFF == ref & 0xFFFF                           # the half-word the packed loads deliver
