@@ -613,6 +613,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ uint32_t s_cst[16];
+    __shared__ uint2 s_keys[DRAIN == 10 ? 2 : 1][DRAIN == 10 ? 4 : 1][DRAIN == 10 ? 3 : 1][DRAIN == 10 ? 2 : 1][DRAIN == 10 ? 32 : 1];   // variant 10: unit parity x quadrant x part 1..3 x row half x lane
     // read back after the first __syncthreads (variant 9 stores two columns per register)
     if (DRAIN >= 6 && threadIdx.x < 16) s_cst[threadIdx.x] = DENORM ? (T9_MAGIC | (T9_MAGIC << 16)) : T6_MAGIC;
     constexpr uint32_t NDW = (DRAIN == 4 || DRAIN == 5 || DRAIN == 7) ? 24u : 16u;   // draining warps
@@ -1000,20 +1001,52 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             uint32_t nfull = (n2 >= c0 + cw) ? (n2 - c0 - cw) / (uint32_t)T4_NCOLS + 1u : 0u;
             if (nfull > ntiles) nfull = ntiles;
             if (dbg & ~(32 | 4)) nfull = 0;   // the timing switches live in the general step
-            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+            // Variant 10 merges the four column parts of a row before they leave the SM: parts 1..3 of a quadrant put their two
+            // keys in shared memory, the four warps meet at a named barrier (once per unit, 42 steps), and part 0's warp writes ONE
+            // key pair per row — a quarter of the matcher's output and of what the fix pass reads, whose merge loop disappears.
+            constexpr bool MERGE = DRAIN == 10;
+            uint32_t ulocal = 0;
+            for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ulocal++) {
                 const uint32_t p = u / qblocks, qb = (u % qblocks) * TC_QROWS + quad * 32 + lane;
                 uint32_t r0[2] = {0u, 0u}, r1[2] = {0u, 0u};   // per row half: packed (odd-column group, even-column group) keys
                 if (wide) t6_unit<true, DRAIN == 10>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
                 else t6_unit<false, DRAIN == 10>(lane_base, bar_tfull, bar_tempty, g, lane, c0, cw, n2, ntiles, nfull, ra, rb, cst, r0, r1, dbg, trole);
+                uint2 mine[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
+                    // four group keys (even / odd columns x best / second): the two smallest go to the fix kernel
+                    const uint32_t ka = t6_group_key(r0[h] & 0xffffu, c0, 0u), kb = t6_group_key(r0[h] >> 16, c0, 1u);
+                    const uint32_t kc = t6_group_key(r1[h] & 0xffffu, c0, 0u), kd = t6_group_key(r1[h] >> 16, c0, 1u);
+                    const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
+                    mine[h] = make_uint2(lo1, min(hi1, lo2));   // ka < kc and kb < kd
                     const uint32_t q = qb + h * 128;
-                    if (q < n1) {
-                        // four group keys (even / odd columns x best / second): the two smallest go to the fix kernel
-                        const uint32_t ka = t6_group_key(r0[h] & 0xffffu, c0, 0u), kb = t6_group_key(r0[h] >> 16, c0, 1u);
-                        const uint32_t kc = t6_group_key(r1[h] & 0xffffu, c0, 0u), kd = t6_group_key(r1[h] >> 16, c0, 1u);
-                        const uint32_t lo1 = min(ka, kb), hi1 = max(ka, kb), lo2 = min(kc, kd);
-                        part[((size_t)p * T4_PARTS + cp) * n1 + q] = make_uint2(lo1, min(hi1, lo2));   // ka < kc and kb < kd
+                    if (!MERGE && q < n1) part[((size_t)p * T4_PARTS + cp) * n1 + q] = mine[h];
+                }
+                if (MERGE) {
+                    if (cp != 0) {
+                        s_keys[ulocal & 1][quad][cp - 1][0][lane] = mine[0];
+                        s_keys[ulocal & 1][quad][cp - 1][1][lane] = mine[1];
+                    }
+                    // the quadrant's four draining warps (immediate barrier ids: with a register id ptxas reserves all sixteen
+                    // hardware barriers of the SM and nothing that calls __syncthreads could run beside this kernel)
+                    if (quad == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else if (quad == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else if (quad == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+                    else asm volatile("bar.sync 4, 128;" ::: "memory");
+                    if (cp == 0) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t k1 = mine[h].x, k2 = mine[h].y;
+#pragma unroll
+                            for (int sp = 0; sp < 3; sp++) {
+                                const uint2 v = s_keys[ulocal & 1][quad][sp][h][lane];
+                                const uint32_t lo = min(k1, v.x), hi = max(k1, v.x);   // v.x < v.y and k1 < k2
+                                k2 = min(min(k2, v.y), hi);
+                                k1 = lo;
+                            }
+                            const uint32_t q = qb + h * 128;
+                            if (q < n1) part[(size_t)p * n1 + q] = make_uint2(k1, k2);
+                        }
                     }
                 }
             }
@@ -1403,7 +1436,7 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     // (vb_knn2_hamming; match_features never looks at it) take variant 1
     if (drain == 7 && div_up(n2, (uint32_t)T4_NCOLS) > T7_MAX_TILES) drain = 6;
     if (drain >= 6 && (div_up(n2, (uint32_t)T4_NCOLS) > T6_MAX_TILES || need_second_index)) drain = 1;
-    const uint32_t nparts = fp4 ? (drain == 3 ? 2u : (drain == 5 || drain == 7) ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
+    const uint32_t nparts = fp4 ? (drain == 10 ? 1u : drain == 3 ? 2u : (drain == 5 || drain == 7) ? 3u : drain == 4 ? 6u : (uint32_t)T4_PARTS) : (uint32_t)TC_COLSPLIT;
     if ((rc = ctx->ws_ensure(WS_KNN_PART, (size_t)P * (nparts + 1) * n1 * sizeof(uint2)))) return rc;
     uint8_t *E = ctx->ws[WS_EXP].as<uint8_t>();
     uint8_t *Eq = E, *Et;
