@@ -733,7 +733,7 @@ def test_kdtree_batched_build_equals_single_builds(ctx, oracle):
 @pytest.mark.parametrize("opts", [dict(count_packed=0, score_packed=0, hamming_fp4=0), dict(tc_fix8=0), dict(hamming_qpt=1, hamming_tc=0),
                                   dict(hamming_qpt=4, hamming_tc=0), dict(tc_drain=1), dict(tc_drain=2), dict(tc_drain=3),
                                   dict(tc_drain=4), dict(tc_drain=5), dict(tc_drain=6), dict(tc_drain=7), dict(tc_drain=8), dict(tc_drain=9),
-                                  dict(tc_drain=10), dict(tc_drain=6, tc_issuers=2)])
+                                  dict(tc_drain=10), dict(tc_drain=6, tc_issuers=2), dict(tc_fix_skip=0)])
 def test_alternative_kernels_agree_with_oracle(ctx, oracle, opts):
     """The code paths behind vb_set_option — k_count<2> / k_score<2> (scalar-instruction versions), the fp8 matcher, the
     two-group fix pass on the match path, the popcount matcher's queries-per-thread variants — still agree with the oracle."""

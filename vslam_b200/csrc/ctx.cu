@@ -80,7 +80,7 @@ int vb_destroy(vb_ctx *c) {
 // force each of them); the second group exists only in a -DVB_TUNING build (measurement aids: timing floors, schedules).
 static const char *const kOptions[] = {
     "hamming_tc", "hamming_fp4", "tc_fix8", "hamming_qpt", "l2_tc", "ransac_lazy", "ransac_prune", "prune_first_chunks",
-    "prune_first16", "prune_growth16", "prune_rounds", "prune_item_chunks", "count_packed", "score_packed", "kd_lanes_per_query", "tc_drain", "tc_svc_hi", "tc_issuers", "pairs_overlap",
+    "prune_first16", "prune_growth16", "prune_rounds", "prune_item_chunks", "count_packed", "score_packed", "kd_lanes_per_query", "tc_drain", "tc_svc_hi", "tc_issuers", "tc_fix_skip", "pairs_overlap",
 #ifdef VB_TUNING
     "tc_dbg", "prune_ctas_per_sm", "pairs_twin", "pairs_split",
 #endif

@@ -269,7 +269,7 @@ int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const
     uint32_t nsplits = pl.nsplits;
     const uint2 *part = nullptr;
     if (hamming_tc_eligible(ctx, pl)) {
-        int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words, &part, fin.knn_idx != nullptr);
+        int rc = hamming_tc_launch(ctx, pl, d1, d2, stride_words, &part, fin.knn_idx != nullptr, fin.ratio);
         if (rc) return rc;
         nsplits = 1;
     } else {

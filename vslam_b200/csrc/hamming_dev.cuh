@@ -34,9 +34,10 @@ struct KnnFinishArgs {
 int hamming_plan(vb_ctx *ctx, uint32_t P, uint32_t n1, uint32_t n2, uint32_t bytes, HammingPlan *pl);
 // tensor-core path (hamming_tc.cu): 256-bit descriptors; *final_part = [P][n1] keys (one split) inside WS_KNN_PART
 bool hamming_tc_eligible(const vb_ctx *ctx, const HammingPlan &pl);
-// need_second_index = false: the second neighbour's key carries its exact distance but only its group's first column
+// need_second_index = false: the second neighbour's key carries its exact distance but only its group's first column, and
+// queries that are certain to fail Lowe's test with `ratio` (>= 0) keep their group keys unevaluated
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
-                      const uint2 **final_part, bool need_second_index);
+                      const uint2 **final_part, bool need_second_index, double ratio);
 int hamming_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
                    KnnFinishArgs fin);
 

@@ -1332,7 +1332,7 @@ k_knn2_tc4(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 template <int LANES, int STRIDE = 1>
 __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict__ d1_base, const uint32_t *__restrict__ d2_base,
                                                      size_t stride_words, uint32_t n1, uint32_t n2, uint32_t nparts,
-                                                     const uint2 *__restrict__ part, uint2 *__restrict__ out) {
+                                                     const uint2 *__restrict__ part, uint2 *__restrict__ out, double ratio) {
     static_assert(TC_GROUP == 8 && (LANES == 8 || LANES == 16), "groups of eight lanes per query");
     const uint32_t sub = threadIdx.x & (LANES - 1);
     const uint32_t q = blockIdx.x * (blockDim.x / LANES) + (threadIdx.x / LANES), p = blockIdx.y;
@@ -1346,7 +1346,13 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
             k2 = min(min(k2, v.y), hi);
             k1 = lo;
         }
-        const uint32_t gk = (sub < 8) ? k1 : k2;
+        // ratio >= 0 (LANES = 8, the caller applies Lowe's test with this ratio and never looks at a failing query's indices):
+        // the second neighbour is at most as far as the other group's best member, so a query that fails the test against
+        // THAT distance — the very comparison k_knn2_finish makes, monotone in the second distance — fails it for certain;
+        // its descriptors are not read and the group keys go out as they are (exact nearest distance, a bound for the second).
+        const bool skip = LANES == 8 && ratio >= 0.0 && k2 != 0xffffffffu &&
+                          !((double)(float)(k1 >> KNN_IDX_BITS) < (double)(float)(k2 >> KNN_IDX_BITS) * ratio);
+        const uint32_t gk = skip ? 0xffffffffu : (sub < 8) ? k1 : k2;
         const uint32_t col = (gk & KNN_IDX_MASK) + (sub & 7) * STRIDE;
         if (LANES == 8) other = k2;
         const uint4 *a = reinterpret_cast<const uint4 *>(d1_base + (size_t)p * stride_words + (size_t)q * 8);
@@ -1357,7 +1363,11 @@ __global__ void __launch_bounds__(256) k_knn2_tc_fix(const uint32_t *__restrict_
                                __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
             key = (d << KNN_IDX_BITS) | col;
         }
-        if (STRIDE == 2 && LANES == 8 && k2 != 0xffffffffu && (k2 >> KNN_IDX_BITS) == (k1 >> KNN_IDX_BITS) &&
+        if (skip) {
+            key = k1;
+            other = k2;
+        }
+        if (STRIDE == 2 && LANES == 8 && !skip && k2 != 0xffffffffu && (k2 >> KNN_IDX_BITS) == (k1 >> KNN_IDX_BITS) &&
             (k2 & KNN_IDX_MASK) == (k1 & KNN_IDX_MASK) + 1u) {
             // the odd group of the best group's span ties with it: its members interleave with the best group's
             const uint32_t col2 = (k2 & KNN_IDX_MASK) + (sub & 7) * 2u;
@@ -1398,7 +1408,7 @@ bool hamming_tc_eligible(const vb_ctx *ctx, const HammingPlan &pl) {
 static bool hamming_tc_use_fp4(const vb_ctx *ctx) { return ctx->opt("hamming_fp4", 1) != 0; }
 
 int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, const uint32_t *d2, size_t stride_words,
-                      const uint2 **final_part, bool need_second_index) {
+                      const uint2 **final_part, bool need_second_index, double ratio) {
     const bool fp4 = hamming_tc_use_fp4(ctx);
     if (!(ctx->func_attr_done & 1u)) {   // a function attribute is per device: remembered per context, not per process
         VB_CUDA(cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -1517,15 +1527,16 @@ int hamming_tc_launch(vb_ctx *ctx, const HammingPlan &pl, const uint32_t *d1, co
     ctx->prof_end("hamming");
     ctx->prof_begin("knnfix");
     const bool fix8 = ctx->opt("tc_fix8", 1) != 0;
+    const double fix_ratio = (need_second_index || ctx->opt("tc_fix_skip", 1) == 0) ? -1.0 : ratio;   // < 0: every query is evaluated
     const bool stride2 = fp4 && drain >= 6;
     if ((need_second_index || !fix8) && stride2)
-        k_knn2_tc_fix<16, 2><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+        k_knn2_tc_fix<16, 2><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed, fix_ratio);
     else if (need_second_index || !fix8)
-        k_knn2_tc_fix<16><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+        k_knn2_tc_fix<16><<<dim3(div_up(n1, 16), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed, fix_ratio);
     else if (stride2)
-        k_knn2_tc_fix<8, 2><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+        k_knn2_tc_fix<8, 2><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed, fix_ratio);
     else
-        k_knn2_tc_fix<8><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed);
+        k_knn2_tc_fix<8><<<dim3(div_up(n1, 32), P), 256, 0, ctx->stream>>>(d1, d2, stride_words, n1, n2, nparts, part, fixed, fix_ratio);
     ctx->prof_end("knnfix");
     ctx->launches += 2;
     VB_CUDA(cudaGetLastError());
